@@ -1,0 +1,545 @@
+// shade.cu -- PBR fragment shading of the compacted G-buffer (rows a4, a5 of SURVEY.md section 8).
+//
+//   dm_shade_mc_fwd        models/materials/dreammat_material.py:615-677 (shade_raytracing), with
+//                          :554-573 sample_diffuse_directions, :575-596 sample_specular_directions,
+//                          :599-604 distribution_ggx, :519-530 geometry_schlick(_ggx),
+//                          :509-517 fresnel_schlick(_directions), :490-507 get_lights,
+//                          :439-455 get_envirmentlight_blender, :110-123 material_smoothness_grad
+//   dm_shade_splitsum_fwd  dreammat_material.py:679-711 (shade_splitsum)
+//   dm_shade_bwd           what torch autograd does for either branch, in closed form
+//
+// Design (B200-first).  The reference materialises >= 40 tensors of shape [pn,328,{1,3}] per view
+// and keeps them for autograd.  Here one WARP owns one covered pixel: lanes stride over the 328
+// light samples, each lane builds its direction, evaluates the BRDF terms, walks the BVH for
+// occlusion (any-hit) and fetches one env-map texel; partial sums are folded with warp
+// shuffles.  The derivative of the colour w.r.t. the five material scalars is carried
+// FORWARD through the same pass (dual numbers in the roughness `a`, which is the only input
+// the sampled directions depend on), so the backward is a 9-float-per-pixel Jacobian product
+// and no ray is traced twice.  HBM traffic per pixel: 56 B of G-buffer/feature reads (staged
+// through shared memory with coalesced loads), 12-108 B of outputs, plus one 16 B texel per
+// unoccluded sample out of a float4-padded lat-long map (one 32 B sector per fetch).
+#include <math_constants.h>
+#include "bvh.cuh"
+
+namespace {
+
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float TWO_PI_F = 6.28318530717958647692f;
+
+struct Dual {
+    float v, d;
+};
+__device__ __forceinline__ Dual mkd(float v, float d = 0.f) { Dual r; r.v = v; r.d = d; return r; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return mkd(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return mkd(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return mkd(a.v * b.v, a.d * b.v + a.v * b.d); }
+__device__ __forceinline__ Dual operator+(Dual a, float b) { return mkd(a.v + b, a.d); }
+__device__ __forceinline__ Dual operator-(Dual a, float b) { return mkd(a.v - b, a.d); }
+__device__ __forceinline__ Dual operator-(float a, Dual b) { return mkd(a - b.v, -b.d); }
+__device__ __forceinline__ Dual operator*(Dual a, float b) { return mkd(a.v * b, a.d * b); }
+__device__ __forceinline__ Dual operator*(float b, Dual a) { return mkd(a.v * b, a.d * b); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+    float q = a.v / b.v;
+    return mkd(q, (a.d - q * b.d) / b.v);
+}
+__device__ __forceinline__ Dual operator/(Dual a, float b) { return mkd(a.v / b, a.d / b); }
+__device__ __forceinline__ Dual dsqrt(Dual a) {
+    float s = sqrtf(a.v);
+    return mkd(s, s > 0.0f ? a.d / (2.0f * s) : 0.0f);
+}
+// torch.clamp(x, 0, 1): gradient passes where 0 <= x <= 1
+__device__ __forceinline__ Dual dclamp01(Dual a) {
+    bool in = (a.v >= 0.0f) && (a.v <= 1.0f);
+    return mkd(fminf(fmaxf(a.v, 0.0f), 1.0f), in ? a.d : 0.0f);
+}
+__device__ __forceinline__ Dual dpow5(Dual a) {
+    float a2 = a.v * a.v, a4 = a2 * a2;
+    return mkd(a4 * a.v, 5.0f * a4 * a.d);
+}
+struct D3 {
+    Dual x, y, z;
+};
+__device__ __forceinline__ Dual ddot(D3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Dual ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// distribution_ggx (:599-604): a2 / (pi * (NoH^2 (a2-1) + 1)^2 + 1e-4)
+__device__ __forceinline__ Dual ggx_D(Dual NoH, Dual a) {
+    Dual a2 = a * a;
+    Dual den = NoH * NoH * (a2 - 1.0f) + 1.0f;
+    return a2 / (PI_F * (den * den) + 1e-4f);
+}
+// geometry_schlick_ggx (:519-525): c / (c (1-k) + k + 1e-5), k = a/2
+__device__ __forceinline__ Dual ggx_G1(Dual c, Dual a) {
+    Dual k = a * 0.5f;
+    return c / (c * (1.0f - k) + k + 1e-5f);
+}
+
+// get_envirmentlight_blender (:439-455): nearest texel of the lat-long map
+__device__ __forceinline__ float4 env_fetch(const float4* __restrict__ env, int H, int W, f3 d) {
+    float inv = 1.0f / sqrtf(dot3(d, d));
+    float x = d.x * inv, y = d.y * inv, z = d.z * inv;
+    float theta = acosf(z);
+    float phi = atan2f(y, x);
+    phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;  // torch.remainder(phi, 2 pi)
+    float u = -phi / TWO_PI_F + 0.5f;
+    float v = theta / PI_F;
+    float fx = u * (float)W; fx = fx - floorf(fx / (float)W) * (float)W;
+    float fy = v * (float)H; fy = fy - floorf(fy / (float)H) * (float)H;
+    int ix = min(max((int)fx, 0), W - 1);
+    int iy = min(max((int)fy, 0), H - 1);
+    return __ldg(env + (int64_t)iy * W + ix);
+}
+
+struct PixelIn {
+    f3 p, n, v;
+    float m[5], mj[5];
+};
+
+constexpr int MC_WARPS = 8;
+
+struct McParams {
+    dm_material_cfg cfg;
+    BvhView bvh;
+    const float4* env; int envH, envW;
+    const float* tab_d; const float* tab_s;
+    const float *pts, *normals, *viewdirs, *features, *features_jitter, *rand_d, *rand_s;
+    int64_t n;
+    float *color, *jac, *reg_sums;
+    float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
+    uint32_t* hit_bits;
+};
+
+__global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
+    extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
+    __shared__ float s_in[MC_WARPS][20];
+    __shared__ float s_reg[2];
+    const int nd = P.cfg.n_diffuse, ns = P.cfg.n_specular, S = nd + ns;
+    float* s_td = s_tab;
+    float* s_ts = s_tab + 3 * nd;
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) {
+        float ua = P.tab_d[2 * i], ue = P.tab_d[2 * i + 1];
+        s_td[3 * i] = ua * PI_F * 2.0f;            // az = az * pi * 2 (:563)
+        s_td[3 * i + 1] = sqrtf(ue + 1e-7f);       // el_sqrt (:564)
+        s_td[3 * i + 2] = sqrtf(1.0f - ue + 1e-7f);  // coeff_z (:567)
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        s_ts[2 * i] = PI_F * 2.0f * P.tab_s[2 * i];  // phi = pi * 2 * az (:583)
+        s_ts[2 * i + 1] = P.tab_s[2 * i + 1];
+    }
+    if (threadIdx.x < 2) s_reg[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pix = (int64_t)blockIdx.x * MC_WARPS + warp;
+    float reg_kd = 0.f, reg_ks = 0.f;
+    if (pix < P.n) {
+        // coalesced staging of the 19 per-pixel input floats through shared memory
+        if (lane < 3) s_in[warp][lane] = P.pts[3 * pix + lane];
+        else if (lane < 6) s_in[warp][lane] = P.normals[3 * pix + lane - 3];
+        else if (lane < 9) s_in[warp][lane] = P.viewdirs[3 * pix + lane - 6];
+        else if (lane < 14) s_in[warp][lane] = P.features[5 * pix + lane - 9];
+        else if (lane < 19) s_in[warp][lane] = P.features_jitter[5 * pix + lane - 14];
+        __syncwarp();
+        const float* si = s_in[warp];
+        const f3 p = mk3(si[0], si[1], si[2]), n = mk3(si[3], si[4], si[5]), v = mk3(si[6], si[7], si[8]);
+        float m[5], mj[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(si[9 + k]); mj[k] = sigmoidf_(si[14 + k]); }
+        // material_smoothness_grad (:110-123)
+        {
+            float k0 = fabsf(m[0] - mj[0]), k1 = fabsf(m[1] - mj[1]), k2 = fabsf(m[2] - mj[2]);
+            reg_kd = ((k0 + k1 + k2) / 3.0f) * k2;
+            reg_ks = fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
+        }
+        const float alb[3] = {fminf(fmaxf(m[0], 0.f), 1.f), fminf(fmaxf(m[1], 0.f), 1.f), fminf(fmaxf(m[2], 0.f), 1.f)};
+        const float met = m[3] * (P.cfg.max_metallic - P.cfg.min_metallic) + P.cfg.min_metallic;
+        const float a = m[4] * (P.cfg.max_roughness - P.cfg.min_roughness) + P.cfg.min_roughness;
+        const float ndv = dot3(v, n);
+        const f3 r = (ndv * n) * 2.0f - v;  // reflections (:620)
+        const float NoV = fminf(fmaxf(ndv, 0.f), 1.f);
+        const f3 xd = ortho_dir(n), yd = cross3(n, xd);
+        const f3 xs = ortho_dir(r), ys = cross3(r, xs);
+        const float rd_ = P.rand_d[pix] * PI_F * 2.0f, rs_ = P.rand_s[pix] * PI_F * 2.0f;
+        const float kd_pdf = (float)nd / (float)(ns + nd), ks_pdf = (float)ns / (float)(ns + nd);
+        const Dual aD = mkd(a, 1.0f);
+        const Dual G1v = ggx_G1(mkd(NoV), aD);
+
+        float Ld[3] = {0, 0, 0}, Ls[3] = {0, 0, 0};
+        float U[3] = {0, 0, 0}, V[3] = {0, 0, 0};      // sum L*w, sum L*w*fh
+        float Ud[3] = {0, 0, 0}, Vd[3] = {0, 0, 0};    // d/da of the above with fh held fixed
+        float Wd[3] = {0, 0, 0};                       // sum L*w*dfh/da
+        uint32_t hitword = 0;
+
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int s = s0 + lane;
+            bool hit = true;
+            if (s < S) {
+                D3 d;
+                const bool spec = s >= nd;
+                if (!spec) {
+                    float az = s_td[3 * s] + rd_;
+                    az = az - floorf(az / TWO_PI_F) * TWO_PI_F;  // % (2 pi)
+                    float sn, cs;
+                    sincosf(az, &sn, &cs);
+                    float cx = s_td[3 * s + 1] * cs, cy = s_td[3 * s + 1] * sn, cz = s_td[3 * s + 2];
+                    f3 dv = cx * xd + cy * yd + cz * n;
+                    d.x = mkd(dv.x); d.y = mkd(dv.y); d.z = mkd(dv.z);
+                } else {
+                    const int j = s - nd;
+                    float ue = s_ts[2 * j + 1];
+                    float phi = s_ts[2 * j] + rs_;
+                    phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
+                    float sn, cs;
+                    sincosf(phi, &sn, &cs);
+                    // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
+                    Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
+                    Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
+                    Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
+                    Dual cx = st * cs, cy = st * sn;
+                    d.x = cx * xs.x + cy * ys.x + ct * r.x;
+                    d.y = cx * xs.y + cy * ys.y + ct * r.y;
+                    d.z = cx * xs.z + cy * ys.z + ct * r.z;
+                }
+                const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+                // half vector H = normalize(v + d) (:513-514)
+                D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;
+                Dual hl2 = ddot(h, h);
+                Dual hl = dsqrt(hl2);
+                float hlc = fmaxf(hl.v, 1e-12f);
+                Dual hinv = mkd(1.0f / hlc, (hl.v > 1e-12f) ? (-hl.d / (hlc * hlc)) : 0.0f);
+                D3 Hh; Hh.x = h.x * hinv; Hh.y = h.y * hinv; Hh.z = h.z * hinv;
+                Dual HoV = dclamp01(ddot(Hh, v));
+                Dual fh = dpow5(dclamp01(1.0f - HoV));
+                Dual NoL = dclamp01(ddot(d, n));
+                Dual NoH = dclamp01(ddot(Hh, n));
+                Dual Dg = ggx_D(NoH, aD);
+                Dual G = G1v * ggx_G1(NoL, aD);
+                Dual pdf;
+                if (!spec) pdf = mkd(NoL.v / PI_F * kd_pdf);
+                else pdf = Dg * NoH / (4.0f * HoV + 1e-5f) * ks_pdf;
+                Dual w = Dg * G / (4.0f * NoV * pdf + 1e-5f);
+                // occlusion + light (:490-507)
+                f3 o = p + dv * 1e-5f;
+                float bt, bu, bvv; int bid;
+                hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+                if (!hit) {
+                    float4 L4 = env_fetch(P.env, P.envH, P.envW, dv);
+                    const float L[3] = {L4.x, L4.y, L4.z};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (!spec) Ld[c] += L[c]; else Ls[c] += L[c];
+                        float lw = L[c] * w.v;
+                        U[c] += lw; V[c] += lw * fh.v;
+                        float lwd = L[c] * w.d;
+                        Ud[c] += lwd; Vd[c] += lwd * fh.v;
+                        Wd[c] += lw * fh.d;
+                    }
+                }
+            }
+            if (P.hit_bits) {
+                uint32_t b = __ballot_sync(0xffffffffu, hit && (s < S));
+                if (lane == (s0 >> 5)) hitword = b;
+            }
+        }
+        if (P.hit_bits && lane < (S + 31) / 32) P.hit_bits[pix * ((S + 31) / 32) + lane] = hitword;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Ld[c] = warp_sum(Ld[c]); Ls[c] = warp_sum(Ls[c]);
+            U[c] = warp_sum(U[c]); V[c] = warp_sum(V[c]);
+            Ud[c] = warp_sum(Ud[c]); Vd[c] = warp_sum(Vd[c]); Wd[c] = warp_sum(Wd[c]);
+        }
+        if (lane == 0) {
+            const float invS = 1.0f / (float)S, invd = 1.0f / (float)nd, invs = 1.0f / (float)ns;
+            float colv[3], specv[3], diffv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float F0 = 0.04f * (1.0f - met) + met * alb[c];
+                float spec = (F0 * (U[c] - V[c]) + V[c]) * invS;
+                float diff = alb[c] * (Ld[c] * invd);
+                float lin = diff + spec;
+                float g = lin2srgb_grad(lin);
+                float dS_dF0 = (U[c] - V[c]) * invS;
+                float dS_da = (F0 * (Ud[c] - Vd[c]) + Vd[c] + (1.0f - F0) * Wd[c]) * invS;
+                colv[c] = lin2srgb_f(lin); specv[c] = spec; diffv[c] = diff;
+                P.jac[9 * pix + 3 * c + 0] = g * (Ld[c] * invd + dS_dF0 * met);          // d/d albedo_c
+                P.jac[9 * pix + 3 * c + 1] = g * (dS_dF0 * (alb[c] - 0.04f));            // d/d metallic
+                P.jac[9 * pix + 3 * c + 2] = g * dS_da;                                   // d/d a
+            }
+            st3(P.color, pix, mk3(colv[0], colv[1], colv[2]));
+            if (P.albedo) st3(P.albedo, pix, mk3(lin2srgb_f(alb[0]), lin2srgb_f(alb[1]), lin2srgb_f(alb[2])));
+            if (P.roughness) P.roughness[pix] = sqrtf(a + 1e-7f);
+            if (P.metalness) P.metalness[pix] = met;
+            if (P.spec_light) st3(P.spec_light, pix, mk3(lin2srgb_f(Ls[0] * invs), lin2srgb_f(Ls[1] * invs), lin2srgb_f(Ls[2] * invs)));
+            if (P.diff_light) st3(P.diff_light, pix, mk3(lin2srgb_f(Ld[0] * invd), lin2srgb_f(Ld[1] * invd), lin2srgb_f(Ld[2] * invd)));
+            if (P.spec_color) st3(P.spec_color, pix, mk3(lin2srgb_f(specv[0]), lin2srgb_f(specv[1]), lin2srgb_f(specv[2])));
+            if (P.diff_color) st3(P.diff_color, pix, mk3(lin2srgb_f(diffv[0]), lin2srgb_f(diffv[1]), lin2srgb_f(diffv[2])));
+            atomicAdd(&s_reg[0], reg_kd);
+            atomicAdd(&s_reg[1], reg_ks);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && P.reg_sums) atomicAdd(P.reg_sums + threadIdx.x, s_reg[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------ split-sum
+
+struct SsParams {
+    dm_material_cfg cfg;
+    const float* lut; int lut_res;
+    const float* dcube; int dres;
+    const float* mips[8]; int n_mips; int res0;
+    const float *normals, *viewdirs, *features, *features_jitter;
+    int64_t n;
+    float *color, *jac, *reg_sums;
+    float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
+};
+
+__device__ __forceinline__ f3 cube_dir(int s, float x, float y) {
+    switch (s) {
+        case 0: return mk3(1.f, -y, -x);
+        case 1: return mk3(-1.f, -y, x);
+        case 2: return mk3(x, 1.f, y);
+        case 3: return mk3(x, -1.f, -y);
+        case 4: return mk3(x, -y, 1.f);
+        default: return mk3(-x, -y, -1.f);
+    }
+}
+__device__ __forceinline__ void dir_cube(f3 d, int& face, float& s, float& t) {
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    float ma;
+    if (ax >= ay && ax >= az) { face = d.x >= 0 ? 0 : 1; ma = ax; }
+    else if (ay >= az) { face = d.y >= 0 ? 2 : 3; ma = ay; }
+    else { face = d.z >= 0 ? 4 : 5; ma = az; }
+    float sv = (face == 0) ? -d.z : (face == 1) ? d.z : (face == 5) ? -d.x : d.x;
+    float tv = (face == 2) ? d.z : (face == 3) ? -d.z : -d.y;
+    s = sv / ma; t = tv / ma;
+}
+// seamless texel fetch (edge texels come from the neighbouring face, corner texels are dropped)
+__device__ __forceinline__ bool cube_texel(const float* __restrict__ cube, int res, int face, int ix, int iy, f3& val) {
+    bool inx = ix >= 0 && ix < res, iny = iy >= 0 && iy < res;
+    if (!(inx || iny)) { val = mk3(0, 0, 0); return false; }
+    if (!(inx && iny)) {
+        float s = ((float)ix + 0.5f) / (float)res * 2.0f - 1.0f, t = ((float)iy + 0.5f) / (float)res * 2.0f - 1.0f;
+        f3 d = cube_dir(face, s, t);
+        float s2, t2;
+        dir_cube(d, face, s2, t2);
+        ix = min(max((int)floorf((s2 + 1.0f) * 0.5f * (float)res), 0), res - 1);
+        iy = min(max((int)floorf((t2 + 1.0f) * 0.5f * (float)res), 0), res - 1);
+    }
+    const float* p = cube + (((int64_t)face * res + iy) * res + ix) * 3;
+    val = mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+    return true;
+}
+__device__ __forceinline__ f3 cube_linear(const float* __restrict__ cube, int res, f3 d) {
+    int face; float s, t;
+    dir_cube(d, face, s, t);
+    float x = (s + 1.0f) * 0.5f * (float)res - 0.5f, y = (t + 1.0f) * 0.5f * (float)res - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = (int)x0f, y0 = (int)y0f;
+    f3 acc = mk3(0, 0, 0); float ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int dx = k & 1, dy = k >> 1;
+        float w = (dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy);
+        f3 val;
+        if (cube_texel(cube, res, face, x0 + dx, y0 + dy, val)) { acc = acc + val * w; ws += w; }
+    }
+    return acc * (1.0f / ws);
+}
+
+__global__ void __launch_bounds__(128) shade_splitsum_kernel(SsParams P) {
+    __shared__ float s_reg[2];
+    if (threadIdx.x < 2) s_reg[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float reg_kd = 0.f, reg_ks = 0.f;
+    if (pix < P.n) {
+        f3 n = ld3(P.normals, pix), v = ld3(P.viewdirs, pix);
+        float m[5], mj[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(P.features[5 * pix + k]); mj[k] = sigmoidf_(P.features_jitter[5 * pix + k]); }
+        float k0 = fabsf(m[0] - mj[0]), k1 = fabsf(m[1] - mj[1]), k2 = fabsf(m[2] - mj[2]);
+        reg_kd = ((k0 + k1 + k2) / 3.0f) * k2;
+        reg_ks = fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
+        float alb[3] = {fminf(fmaxf(m[0], 0.f), 1.f), fminf(fmaxf(m[1], 0.f), 1.f), fminf(fmaxf(m[2], 0.f), 1.f)};
+        float met = m[3] * (P.cfg.max_metallic - P.cfg.min_metallic) + P.cfg.min_metallic;
+        float rough = m[4] * (P.cfg.max_roughness - P.cfg.min_roughness) + P.cfg.min_roughness;
+        float ndv = dot3(n, v);
+        f3 refl = (ndv * n) * 2.0f - v;
+        // FG LUT, bilinear, clamp (:686-692); d fg / d rough kept for the Jacobian
+        float fg0, fg1, dfg0, dfg1;
+        {
+            int R = P.lut_res;
+            float x = fminf(fmaxf(ndv, 0.f), 1.f) * R - 0.5f, y = fminf(fmaxf(rough, 0.f), 1.f) * R - 0.5f;
+            float x0f = floorf(x), y0f = floorf(y);
+            float fx = x - x0f, fy = y - y0f;
+            int x0 = min(max((int)x0f, 0), R - 1), x1 = min(max((int)x0f + 1, 0), R - 1);
+            int y0 = min(max((int)y0f, 0), R - 1), y1 = min(max((int)y0f + 1, 0), R - 1);
+            const float2* L = reinterpret_cast<const float2*>(P.lut);
+            float2 a00 = __ldg(L + y0 * R + x0), a01 = __ldg(L + y0 * R + x1), a10 = __ldg(L + y1 * R + x0), a11 = __ldg(L + y1 * R + x1);
+            float t0x = a00.x * (1 - fx) + a01.x * fx, t1x = a10.x * (1 - fx) + a11.x * fx;
+            float t0y = a00.y * (1 - fx) + a01.y * fx, t1y = a10.y * (1 - fx) + a11.y * fx;
+            fg0 = t0x * (1 - fy) + t1x * fy; fg1 = t0y * (1 - fy) + t1y * fy;
+            bool rin = rough >= 0.f && rough <= 1.f;
+            dfg0 = rin ? (t1x - t0x) * R : 0.f; dfg1 = rin ? (t1y - t0y) * R : 0.f;
+        }
+        f3 dl = cube_linear(P.dcube, P.dres, n);
+        // envlight.get_mip + trilinear mip blend; d/d rough through the level
+        float lvl, dlvl;
+        {
+            const float mn = 0.08f, mx = 0.5f; int nm = P.n_mips;
+            if (rough < mx) { float rc = fminf(fmaxf(rough, mn), mx); lvl = (rc - mn) / (mx - mn) * (nm - 2); dlvl = (rough >= mn && rough <= mx) ? (nm - 2) / (mx - mn) : 0.f; }
+            else { float rc = fminf(fmaxf(rough, mx), 1.0f); lvl = (rc - mx) / (1.0f - mx) + nm - 2; dlvl = (rough >= mx && rough <= 1.0f) ? 1.0f / (1.0f - mx) : 0.f; }
+        }
+        float lc = fminf(fmaxf(lvl, 0.f), (float)(P.n_mips - 1));
+        int l0 = min((int)floorf(lc), P.n_mips - 1), l1 = min(l0 + 1, P.n_mips - 1);
+        float fl = lc - (float)l0;
+        f3 s0 = cube_linear(P.mips[l0], P.res0 >> l0, refl);
+        f3 s1 = cube_linear(P.mips[l1], P.res0 >> l1, refl);
+        f3 sl = s0 * (1.0f - fl) + s1 * fl;
+        f3 dsl = (lvl >= 0.f && lvl <= (float)(P.n_mips - 1)) ? (s1 - s0) * dlvl : mk3(0, 0, 0);
+        const float dlv[3] = {dl.x, dl.y, dl.z}, slv[3] = {sl.x, sl.y, sl.z}, dslv[3] = {dsl.x, dsl.y, dsl.z};
+        float colv[3], sa[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float F0 = (1.0f - met) * 0.04f + met * alb[c];
+            sa[c] = F0 * fg0 + fg1;
+            float lin = alb[c] * dlv[c] + sa[c] * slv[c];
+            float g = (lin >= 0.f && lin <= 1.f) ? 1.f : 0.f;
+            colv[c] = fminf(fmaxf(lin, 0.f), 1.f);
+            P.jac[9 * pix + 3 * c + 0] = g * (dlv[c] + met * fg0 * slv[c]);
+            P.jac[9 * pix + 3 * c + 1] = g * ((alb[c] - 0.04f) * fg0 * slv[c]);
+            P.jac[9 * pix + 3 * c + 2] = g * ((F0 * dfg0 + dfg1) * slv[c] + sa[c] * dslv[c]);
+        }
+        st3(P.color, pix, mk3(colv[0], colv[1], colv[2]));
+        if (P.albedo) st3(P.albedo, pix, mk3(alb[0], alb[1], alb[2]));
+        if (P.roughness) P.roughness[pix] = rough;
+        if (P.metalness) P.metalness[pix] = met;
+        if (P.spec_light) st3(P.spec_light, pix, mk3(lin2srgb_f(sl.x), lin2srgb_f(sl.y), lin2srgb_f(sl.z)));
+        if (P.diff_light) st3(P.diff_light, pix, mk3(lin2srgb_f(dl.x), lin2srgb_f(dl.y), lin2srgb_f(dl.z)));
+        if (P.spec_color) st3(P.spec_color, pix, mk3(lin2srgb_f(sa[0]), lin2srgb_f(sa[1]), lin2srgb_f(sa[2])));
+        if (P.diff_color) st3(P.diff_color, pix, mk3(lin2srgb_f(alb[0]), lin2srgb_f(alb[1]), lin2srgb_f(alb[2])));
+    }
+    reg_kd = warp_sum(reg_kd); reg_ks = warp_sum(reg_ks);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_reg[0], reg_kd); atomicAdd(&s_reg[1], reg_ks); }
+    __syncthreads();
+    if (threadIdx.x < 2 && P.reg_sums) atomicAdd(P.reg_sums + threadIdx.x, s_reg[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// dfeatures = sigmoid'(f) * [ J^T dcolor (through the range maps) + d reg / d m ],  dfeatures_jitter = sigmoid'(fj) * d reg / d mj
+__global__ void __launch_bounds__(256) shade_bwd_kernel(dm_material_cfg cfg, const float* __restrict__ features,
+                                                        const float* __restrict__ features_jitter,
+                                                        const float* __restrict__ dcolor,
+                                                        const float* __restrict__ jac, float dreg_kd, float dreg_ks,
+                                                        int64_t n, float* __restrict__ df, float* __restrict__ dfj) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= n) return;
+    float m[5], mj[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(features[5 * pix + k]); mj[k] = sigmoidf_(features_jitter[5 * pix + k]); }
+    float dm[5] = {0, 0, 0, 0, 0}, dmj[5] = {0, 0, 0, 0, 0};
+    const float* J = jac + 9 * pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float g = dcolor[3 * pix + c];
+        dm[c] += g * J[3 * c + 0];  // albedo clamp(0,1) of a sigmoid is the identity with unit slope
+        dm[3] += g * J[3 * c + 1] * (cfg.max_metallic - cfg.min_metallic);
+        dm[4] += g * J[3 * c + 2] * (cfg.max_roughness - cfg.min_roughness);
+    }
+    // smoothness regulariser: kd = |m-mj|[0:3], ks = |m-mj|[3:5]; sign(0) = 0 as in torch.abs backward
+    {
+        float d[5], sg[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { float x = m[k] - mj[k]; d[k] = fabsf(x); sg[k] = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+        float luma = (d[0] + d[1] + d[2]) / 3.0f;
+        float gk[5];
+        gk[0] = dreg_kd * d[2] / 3.0f;
+        gk[1] = dreg_kd * d[2] / 3.0f;
+        gk[2] = dreg_kd * (d[2] / 3.0f + luma);
+        gk[3] = dreg_ks * d[4];
+        gk[4] = dreg_ks * d[3];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { dm[k] += gk[k] * sg[k]; dmj[k] -= gk[k] * sg[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        df[5 * pix + k] = dm[k] * m[k] * (1.0f - m[k]);
+        dfj[5 * pix + k] = dmj[k] * mj[k] * (1.0f - mj[k]);
+    }
+}
+
+__global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f);
+}
+
+}  // namespace
+
+extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, const float* env_rgba, int envH, int envW,
+                               const float* tab_d, const float* tab_s, const float* pts, const float* normals,
+                               const float* viewdirs, const float* features, const float* features_jitter,
+                               const float* rand_d, const float* rand_s, int64_t n, float* color, float* jac,
+                               float* reg_sums, float* albedo, float* roughness, float* metalness, float* spec_light,
+                               float* diff_light, float* spec_color, float* diff_color, uint32_t* hit_bits,
+                               void* stream) {
+    DM_REQUIRE(cfg && bvh && env_rgba && tab_d && tab_s && pts && normals && viewdirs && features && features_jitter &&
+                   rand_d && rand_s && color && jac, "null pointer");
+    DM_REQUIRE(cfg->n_diffuse > 0 && cfg->n_specular > 0 && cfg->n_diffuse + cfg->n_specular <= 4096, "sample counts");
+    if (n == 0) return DM_OK;
+    McParams P;
+    P.cfg = *cfg; P.bvh = BvhView{bvh->nodes, bvh->tris, bvh->root};
+    P.env = (const float4*)env_rgba; P.envH = envH; P.envW = envW; P.tab_d = tab_d; P.tab_s = tab_s;
+    P.pts = pts; P.normals = normals; P.viewdirs = viewdirs; P.features = features; P.features_jitter = features_jitter;
+    P.rand_d = rand_d; P.rand_s = rand_s; P.n = n; P.color = color; P.jac = jac; P.reg_sums = reg_sums;
+    P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
+    P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits;
+    size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float);
+    shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_shade_splitsum_fwd(const dm_material_cfg* cfg, const float* fg_lut, int lut_res,
+                                     const float* diffuse_cube, int diff_res, const float* const* spec_mips_host,
+                                     int n_mips, int spec_res0, const float* normals, const float* viewdirs,
+                                     const float* features, const float* features_jitter, int64_t n, float* color,
+                                     float* jac, float* reg_sums, float* albedo, float* roughness, float* metalness,
+                                     float* spec_light, float* diff_light, float* spec_color, float* diff_color,
+                                     void* stream) {
+    DM_REQUIRE(cfg && fg_lut && diffuse_cube && spec_mips_host && normals && viewdirs && features && features_jitter &&
+                   color && jac, "null pointer");
+    DM_REQUIRE(n_mips >= 2 && n_mips <= 8, "2..8 specular mips");
+    if (n == 0) return DM_OK;
+    SsParams P;
+    P.cfg = *cfg; P.lut = fg_lut; P.lut_res = lut_res; P.dcube = diffuse_cube; P.dres = diff_res;
+    for (int i = 0; i < 8; ++i) P.mips[i] = i < n_mips ? spec_mips_host[i] : nullptr;
+    P.n_mips = n_mips; P.res0 = spec_res0;
+    P.normals = normals; P.viewdirs = viewdirs; P.features = features; P.features_jitter = features_jitter; P.n = n;
+    P.color = color; P.jac = jac; P.reg_sums = reg_sums; P.albedo = albedo; P.roughness = roughness;
+    P.metalness = metalness; P.spec_light = spec_light; P.diff_light = diff_light; P.spec_color = spec_color;
+    P.diff_color = diff_color;
+    shade_splitsum_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(P);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_shade_bwd(const dm_material_cfg* cfg, const float* features, const float* features_jitter,
+                            const float* dcolor, const float* jac, float dreg_kd, float dreg_ks, int64_t n,
+                            float* dfeatures, float* dfeatures_jitter, void* stream) {
+    DM_REQUIRE(cfg && features && features_jitter && dcolor && jac && dfeatures && dfeatures_jitter, "null pointer");
+    if (n == 0) return DM_OK;
+    shade_bwd_kernel<<<(unsigned)dm_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(*cfg, features, features_jitter, dcolor,
+                                                                                   jac, dreg_kd, dreg_ks, n, dfeatures,
+                                                                                   dfeatures_jitter);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_envmap_pack(const float* rgb, int64_t n_texels, float* rgba, void* stream) {
+    DM_REQUIRE(rgb && rgba, "null pointer");
+    if (n_texels == 0) return DM_OK;
+    envmap_pack_kernel<<<(unsigned)dm_ceil_div(n_texels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, n_texels, (float4*)rgba);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}

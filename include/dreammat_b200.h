@@ -1,0 +1,159 @@
+/*
+ * dreammat_b200.h -- C-ABI of the B200-native DreamMat SDS inner loop.
+ *
+ * Drop-in boundary: every entry point replaces one native call the
+ * reference's plugins make into an un-vendored CUDA dependency (nvdiffrast, tiny-cuda-nn,
+ * _raytracing, envlight, diffusers/cuDNN).  The reference file:line each one stands in for
+ * is cited beside it (paths relative to threestudio_dreammat/threestudio/).
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers unless the name ends in _host; row-major, dense;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or a DM_E* code (<0);
+ *     dm_last_error() returns a static string for the calling thread;
+ *   - no hidden allocations on the per-iteration entry points: scratch comes from the caller.
+ */
+#ifndef DREAMMAT_B200_H
+#define DREAMMAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_OK 0
+#define DM_EINVAL (-1)
+#define DM_EUNSUPPORTED (-2)
+#define DM_EDRIVER (-3)
+
+const char* dm_last_error(void);
+int dm_version(void);
+/* device sanity: returns 0 iff device `dev` is compute capability 10.x (sm_100a code present). */
+int dm_device_check(int dev);
+
+/* ------------------------------------------------------------------ geometry: hash grid + MLP
+ * Replaces tcnn.Encoding (HashGrid) + VanillaMLP as called from
+ * models/geometry/dreammat_mesh.py:239-254 via models/networks.py:55-64,150-187. */
+typedef struct {
+    int32_t n_levels;        /* 16 */
+    int32_t n_features;      /* 2 (only value supported) */
+    int32_t log2_hashmap;    /* 19 */
+    int32_t base_resolution; /* 16 */
+    float per_level_scale;   /* 1.447269237440378 */
+    float bbox_min, bbox_max;/* contract_to_unisphere box: -radius, +radius (geometry/base.py:20-32) */
+    int32_t n_hidden;        /* 64 */
+    int32_t n_out;           /* 5 */
+} dm_hashgrid_cfg;
+
+/* host: total number of grid entries (x n_features = params); offsets_host gets n_levels+1 entry offsets */
+int64_t dm_hashgrid_layout(const dm_hashgrid_cfg* cfg, uint32_t* offsets_host);
+/* features[n,n_out] = MLP(HashGrid(contract(points[n,3]))) */
+int dm_hashgrid_mlp_fwd(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid,
+                        const float* W1, const float* W2, float* features, void* stream);
+/* accumulates (+=) into dgrid, dW1, dW2; the forward is recomputed, nothing is saved */
+int dm_hashgrid_mlp_bwd(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid,
+                        const float* W1, const float* W2, const float* dfeatures, float* dgrid, float* dW1,
+                        float* dW2, void* stream);
+/* encoding only ([n, n_levels*n_features]); used by tests to pin the tcnn layout */
+int dm_hashgrid_encode(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid, float* enc,
+                       void* stream);
+
+/* tangent-plane gaussian jitter, models/renderers/raytracing_renderer.py:161-173 */
+int dm_jitter_positions(const float* pos, const float* nrm, const float* rand_ang, const float* normal_eps,
+                        int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------ BVH (replaces _raytracing)
+ * models/renderers/raytracing_renderer.py:20-67 (RayTracer), :318-324 (miss <=> depth >= 10). */
+typedef struct dm_bvh dm_bvh;
+int dm_bvh_build(const float* verts_host, int64_t n_verts, const int32_t* tris_host, int64_t n_tris, dm_bvh** out);
+void dm_bvh_free(dm_bvh* bvh);
+int64_t dm_bvh_num_nodes(const dm_bvh* bvh);
+/* closest hit: t[n] (10.0 on miss), tri[n] (-1 on miss), uv[n,2] (barycentrics of vertex 1, 2); uv may be NULL */
+int dm_bvh_trace(const dm_bvh* bvh, const float* rays_o, const float* rays_d, int64_t n, float* t, int32_t* tri,
+                 float* uv, void* stream);
+
+/* ------------------------------------------------------------------ G-buffer (replaces dr.rasterize + dr.interpolate)
+ * models/renderers/raytracing_renderer.py:122-159, utils/rasterize.py:22-78.  Visibility at
+ * pixel centres by closest hit of the pixel-centre ray; outputs in nvdiffrast's layout.
+ * v_pos/v_nrm [V,3], tris [F,3] int32 (device); rays_o/rays_d [B,H,W,3]; mvp,w2c [B,4,4].
+ * rast [B,H,W,4] = (u,v,z/w,tri_id+1); gb_pos/gb_nrm [B,H*W,3]; mask [B,H*W] uint8;
+ * comp_normal [B,H,W,3] (view-space normal map over bg (.5,.5,1), no antialias). */
+int dm_raster_gbuffer(const dm_bvh* bvh, const float* v_pos, const float* v_nrm, const int32_t* tris,
+                      const float* rays_o, const float* rays_d, const float* mvp, const float* w2c, int B, int H,
+                      int W, float* rast, float* gb_pos, float* gb_nrm, uint8_t* mask, float* comp_normal,
+                      void* stream);
+/* row-major stream compaction of mask -> pixel indices; count_host receives pn.  (init-time; syncs) */
+int dm_compact_mask(const uint8_t* mask, int64_t n, int32_t* idx_out, int64_t* count_host, void* stream);
+/* dst[i,:] = src[idx[i],:] for c floats per row */
+int dm_gather_rows(const float* src, const int32_t* idx, int64_t n, int c, float* dst, void* stream);
+/* depth map, raytracing_renderer.py:129-134: per-batch min/max of 1/(z/w + 1e-6) over mask, -> [0.3,1] */
+int dm_depth_normalize(const float* rast, const uint8_t* mask, int64_t n_pix, float* depth_out, float* scratch2,
+                       void* stream);
+
+/* ------------------------------------------------------------------ material (a4/a5)
+ * models/materials/dreammat_material.py:713-763 */
+typedef struct {
+    float min_metallic, max_metallic;       /* 0.0, 0.9 */
+    float min_roughness, max_roughness;     /* MC: 0.01, 0.9 (roughness^2); split-sum: 0.1, 0.95 */
+    int32_t n_diffuse, n_specular;          /* 200, 128 */
+} dm_material_cfg;
+
+/* Monte-Carlo shading, dreammat_material.py:615-677 (+ :490-507 get_lights, :439-455 env lookup,
+ * :554-596 sampling).  env_rgba: [envH,envW] float4 (rgb + pad) built by dm_envmap_pack.
+ * tab_d [n_diffuse,2], tab_s [n_specular,2]: the (ua,ue) tables of :389-398.
+ * rand_d, rand_s [n]: uniform draws (:567, :590).
+ * Outputs: color [n,3] (sRGB, differentiable), jac [n,9] = d color_c / d (albedo_c, metallic, a)
+ * for c=0..2, reg_sums[2] += (sum luma*|dkd_b|, sum |dks0|*|dks1|); aux pointers may be NULL:
+ * albedo[n,3] roughness[n] metalness[n] spec_light[n,3] diff_light[n,3] spec_color[n,3] diff_color[n,3]. */
+int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, const float* env_rgba, int envH, int envW,
+                    const float* tab_d, const float* tab_s, const float* pts, const float* normals,
+                    const float* viewdirs, const float* features, const float* features_jitter,
+                    const float* rand_d, const float* rand_s, int64_t n, float* color, float* jac,
+                    float* reg_sums, float* albedo, float* roughness, float* metalness, float* spec_light,
+                    float* diff_light, float* spec_color, float* diff_color, uint32_t* hit_bits, void* stream);
+
+/* Split-sum shading, dreammat_material.py:679-711.  fg_lut [256,256,2]; diffuse_cube [6,rd,rd,3];
+ * spec_mips: n_mips device pointers (host array) to [6,r_i,r_i,3], r_i = spec_res0 >> i. */
+int dm_shade_splitsum_fwd(const dm_material_cfg* cfg, const float* fg_lut, int lut_res, const float* diffuse_cube,
+                          int diff_res, const float* const* spec_mips_host, int n_mips, int spec_res0,
+                          const float* normals, const float* viewdirs, const float* features,
+                          const float* features_jitter, int64_t n, float* color, float* jac, float* reg_sums,
+                          float* albedo, float* roughness, float* metalness, float* spec_light, float* diff_light,
+                          float* spec_color, float* diff_color, void* stream);
+
+/* backward of either shading path: dfeatures[n,5], dfeatures_jitter[n,5] (overwritten).
+ * dcolor [n,3]; reg_scale = d loss / d mat_reg_sum terms: dreg_kd = lambda*0.25/n_total, dreg_ks = lambda*0.1/n_total */
+int dm_shade_bwd(const dm_material_cfg* cfg, const float* features, const float* features_jitter,
+                 const float* dcolor, const float* jac, float dreg_kd, float dreg_ks, int64_t n, float* dfeatures,
+                 float* dfeatures_jitter, void* stream);
+
+/* [H,W,3] float -> [H,W] float4 */
+int dm_envmap_pack(const float* rgb, int64_t n_texels, float* rgba, void* stream);
+
+/* ------------------------------------------------------------------ canvas (a6)
+ * raytracing_renderer.py:189-207 without the antialias pass: canvas = 1; canvas[pix[i]] = color[i]. */
+int dm_scatter_canvas(const float* values, const int32_t* pix, int64_t n, int c, float* canvas, void* stream);
+int dm_fill(float* p, int64_t n, float v, void* stream);
+/* dvalues[i,:] = dcanvas[pix[i],:] */
+int dm_gather_canvas_grad(const float* dcanvas, const int32_t* pix, int64_t n, int c, float* dvalues, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (a9)
+ * torch.optim.Adam as configured by systems/utils.py:34-53 + configs/dreammat.yaml:110-115 */
+int dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int32_t step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------ CSD / SDS combine (a8 tail, a9)
+ * models/guidance/dreammat_guidance.py:475-481,584-594.
+ * eps_pred [3,B,C,H,W] (text, uncond, null) fp32; noise, latents [B,C,H,W]; w[B] = 1 - alphas_cumprod[t].
+ * grad = nan_to_num(w*(c*e_text + u*e_uncond + nl*e_null + s*noise)); dlatents = grad / B;
+ * norms[10]: loss_sds, grad_norm, uncond_m_noise, text_m_noise, text_m_uncond, text_m_null,
+ * null_m_uncond, noise, uncond, text (squared sums; sqrt taken by the host). */
+int dm_sds_grad(const float* eps_pred, const float* noise, const float* w, int B, int64_t chw, float c_text,
+                float c_uncond, float c_null, float c_noise, float* grad, float* dlatents, float* norms,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
