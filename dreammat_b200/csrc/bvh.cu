@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(128) bvh_trace_kernel(BvhView bv, const float*
 
 extern "C" int dm_bvh_trace(const dm_bvh* bvh, const float* rays_o, const float* rays_d, int64_t n, float* t,
                             int32_t* tri, float* uv, void* stream) {
-    DM_REQUIRE(bvh && rays_o && rays_d && t && tri, "null pointer");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(bvh && rays_o && rays_d && t && tri, "null pointer");
     BvhView bv{bvh->nodes, bvh->tris, bvh->root};
     bvh_trace_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(bv, rays_o, rays_d, n, t, tri, uv);
     DM_CHECK_LAUNCH();
@@ -212,9 +212,9 @@ extern "C" int dm_raster_gbuffer(const dm_bvh* bvh, const float* v_pos, const fl
                                  const float* rays_o, const float* rays_d, const float* mvp, const float* w2c, int B,
                                  int H, int W, float* rast, float* gb_pos, float* gb_nrm, uint8_t* mask,
                                  float* comp_normal, void* stream) {
+    if ((int64_t)B * H * W == 0) return DM_OK;
     DM_REQUIRE(bvh && v_pos && v_nrm && tris && rays_o && rays_d && mvp && w2c, "null pointer");
     int64_t n = (int64_t)B * H * W;
-    if (n == 0) return DM_OK;
     BvhView bv{bvh->nodes, bvh->tris, bvh->root};
     gbuffer_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
         bv, v_pos, v_nrm, tris, rays_o, rays_d, mvp, w2c, B, (int64_t)H * W, rast, gb_pos, gb_nrm, mask, comp_normal);

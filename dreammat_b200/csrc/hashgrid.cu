@@ -304,10 +304,10 @@ static int check_mlp(const dm_hashgrid_cfg* cfg) {
 
 extern "C" int dm_hashgrid_mlp_fwd(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid,
                                    const float* W1, const float* W2, float* features, void* stream) {
+    if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && points && grid && W1 && W2 && features, "null pointer");
     LevelMeta m; int rc = make_meta(cfg, m, nullptr); if (rc) return rc;
     rc = check_mlp(cfg); if (rc) return rc;
-    if (n == 0) return DM_OK;
     int64_t tiles = dm_ceil_div(n, TILE);
     int grid_dim = (int)(tiles < (int64_t)DM_NUM_SMS * 4 ? tiles : (int64_t)DM_NUM_SMS * 4);
     hashgrid_fwd_kernel<true><<<grid_dim, NTHREADS, 0, (cudaStream_t)stream>>>(m, points, n, (const float2*)grid, W1, W2, features);
@@ -317,10 +317,10 @@ extern "C" int dm_hashgrid_mlp_fwd(const dm_hashgrid_cfg* cfg, const float* poin
 
 extern "C" int dm_hashgrid_encode(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid,
                                   float* enc, void* stream) {
+    if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && points && grid && enc, "null pointer");
     LevelMeta m; int rc = make_meta(cfg, m, nullptr); if (rc) return rc;
     DM_REQUIRE(cfg->n_levels == 16, "encode-only path expects 16 levels");
-    if (n == 0) return DM_OK;
     int64_t tiles = dm_ceil_div(n, TILE);
     int grid_dim = (int)(tiles < (int64_t)DM_NUM_SMS * 4 ? tiles : (int64_t)DM_NUM_SMS * 4);
     hashgrid_fwd_kernel<false><<<grid_dim, NTHREADS, 0, (cudaStream_t)stream>>>(m, points, n, (const float2*)grid, nullptr, nullptr, enc);
@@ -331,10 +331,10 @@ extern "C" int dm_hashgrid_encode(const dm_hashgrid_cfg* cfg, const float* point
 extern "C" int dm_hashgrid_mlp_bwd(const dm_hashgrid_cfg* cfg, const float* points, int64_t n, const float* grid,
                                    const float* W1, const float* W2, const float* dfeatures, float* dgrid, float* dW1,
                                    float* dW2, void* stream) {
+    if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && points && grid && W1 && W2 && dfeatures && dgrid && dW1 && dW2, "null pointer");
     LevelMeta m; int rc = make_meta(cfg, m, nullptr); if (rc) return rc;
     rc = check_mlp(cfg); if (rc) return rc;
-    if (n == 0) return DM_OK;
     int64_t tiles = dm_ceil_div(n, TILE);
     int grid_dim = (int)(tiles < (int64_t)DM_NUM_SMS * 2 ? tiles : (int64_t)DM_NUM_SMS * 2);
     hashgrid_bwd_kernel<<<grid_dim, NTHREADS, 0, (cudaStream_t)stream>>>(m, points, n, (const float2*)grid, W1, W2, dfeatures,
@@ -360,8 +360,8 @@ __global__ void jitter_kernel(const float* __restrict__ pos, const float* __rest
 
 extern "C" int dm_jitter_positions(const float* pos, const float* nrm, const float* rand_ang, const float* normal_eps,
                                    int64_t n, float* out, void* stream) {
-    DM_REQUIRE(pos && nrm && rand_ang && normal_eps && out, "null pointer");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(pos && nrm && rand_ang && normal_eps && out, "null pointer");
     jitter_kernel<<<(unsigned)dm_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, nrm, rand_ang, normal_eps, n, out);
     DM_CHECK_LAUNCH();
     return DM_OK;

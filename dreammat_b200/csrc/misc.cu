@@ -189,8 +189,8 @@ extern "C" int dm_compact_mask(const uint8_t* mask, int64_t n, int32_t* idx_out,
 }
 
 extern "C" int dm_gather_rows(const float* src, const int32_t* idx, int64_t n, int c, float* dst, void* stream) {
-    DM_REQUIRE(src && idx && dst && c > 0, "bad args");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(src && idx && dst && c > 0, "bad args");
     gather_rows_kernel<<<(unsigned)dm_ceil_div(n * c, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, c, dst);
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -201,16 +201,16 @@ extern "C" int dm_gather_canvas_grad(const float* dcanvas, const int32_t* pix, i
 }
 
 extern "C" int dm_scatter_canvas(const float* values, const int32_t* pix, int64_t n, int c, float* canvas, void* stream) {
-    DM_REQUIRE(values && pix && canvas && c > 0, "bad args");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(values && pix && canvas && c > 0, "bad args");
     scatter_rows_kernel<<<(unsigned)dm_ceil_div(n * c, 256), 256, 0, (cudaStream_t)stream>>>(values, pix, n, c, canvas);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_fill(float* p, int64_t n, float v, void* stream) {
-    DM_REQUIRE(p, "null pointer");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(p, "null pointer");
     fill_kernel<<<(unsigned)dm_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -218,8 +218,8 @@ extern "C" int dm_fill(float* p, int64_t n, float v, void* stream) {
 
 extern "C" int dm_depth_normalize(const float* rast, const uint8_t* mask, int64_t n_pix, float* depth_out, float* scratch2,
                                   void* stream) {
-    DM_REQUIRE(rast && mask && depth_out && scratch2, "null pointer");
     if (n_pix == 0) return DM_OK;
+    DM_REQUIRE(rast && mask && depth_out && scratch2, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     depth_init_kernel<<<1, 1, 0, st>>>((int*)scratch2);
     depth_minmax_kernel<<<(unsigned)dm_ceil_div(n_pix, 256), 256, 0, st>>>(rast, mask, n_pix, (int*)scratch2);
@@ -230,8 +230,8 @@ extern "C" int dm_depth_normalize(const float* rast, const uint8_t* mask, int64_
 
 extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                             float eps, int32_t step, float grad_scale, void* stream) {
-    DM_REQUIRE(p && g && m && v && step >= 1, "bad args");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(p && g && m && v && step >= 1, "bad args");
     DM_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "16-byte alignment");
     double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));

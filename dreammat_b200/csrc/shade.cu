@@ -483,10 +483,10 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
                                float* reg_sums, float* albedo, float* roughness, float* metalness, float* spec_light,
                                float* diff_light, float* spec_color, float* diff_color, uint32_t* hit_bits,
                                void* stream) {
+    if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && bvh && env_rgba && tab_d && tab_s && pts && normals && viewdirs && features && features_jitter &&
                    rand_d && rand_s && color && jac, "null pointer");
     DM_REQUIRE(cfg->n_diffuse > 0 && cfg->n_specular > 0 && cfg->n_diffuse + cfg->n_specular <= 4096, "sample counts");
-    if (n == 0) return DM_OK;
     McParams P;
     P.cfg = *cfg; P.bvh = BvhView{bvh->nodes, bvh->tris, bvh->root};
     P.env = (const float4*)env_rgba; P.envH = envH; P.envW = envW; P.tab_d = tab_d; P.tab_s = tab_s;
@@ -507,10 +507,10 @@ extern "C" int dm_shade_splitsum_fwd(const dm_material_cfg* cfg, const float* fg
                                      float* jac, float* reg_sums, float* albedo, float* roughness, float* metalness,
                                      float* spec_light, float* diff_light, float* spec_color, float* diff_color,
                                      void* stream) {
+    if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && fg_lut && diffuse_cube && spec_mips_host && normals && viewdirs && features && features_jitter &&
                    color && jac, "null pointer");
     DM_REQUIRE(n_mips >= 2 && n_mips <= 8, "2..8 specular mips");
-    if (n == 0) return DM_OK;
     SsParams P;
     P.cfg = *cfg; P.lut = fg_lut; P.lut_res = lut_res; P.dcube = diffuse_cube; P.dres = diff_res;
     for (int i = 0; i < 8; ++i) P.mips[i] = i < n_mips ? spec_mips_host[i] : nullptr;
@@ -527,8 +527,8 @@ extern "C" int dm_shade_splitsum_fwd(const dm_material_cfg* cfg, const float* fg
 extern "C" int dm_shade_bwd(const dm_material_cfg* cfg, const float* features, const float* features_jitter,
                             const float* dcolor, const float* jac, float dreg_kd, float dreg_ks, int64_t n,
                             float* dfeatures, float* dfeatures_jitter, void* stream) {
-    DM_REQUIRE(cfg && features && features_jitter && dcolor && jac && dfeatures && dfeatures_jitter, "null pointer");
     if (n == 0) return DM_OK;
+    DM_REQUIRE(cfg && features && features_jitter && dcolor && jac && dfeatures && dfeatures_jitter, "null pointer");
     shade_bwd_kernel<<<(unsigned)dm_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(*cfg, features, features_jitter, dcolor,
                                                                                    jac, dreg_kd, dreg_ks, n, dfeatures,
                                                                                    dfeatures_jitter);
@@ -537,8 +537,8 @@ extern "C" int dm_shade_bwd(const dm_material_cfg* cfg, const float* features, c
 }
 
 extern "C" int dm_envmap_pack(const float* rgb, int64_t n_texels, float* rgba, void* stream) {
-    DM_REQUIRE(rgb && rgba, "null pointer");
     if (n_texels == 0) return DM_OK;
+    DM_REQUIRE(rgb && rgba, "null pointer");
     envmap_pack_kernel<<<(unsigned)dm_ceil_div(n_texels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, n_texels, (float4*)rgba);
     DM_CHECK_LAUNCH();
     return DM_OK;

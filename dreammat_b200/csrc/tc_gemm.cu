@@ -1,0 +1,400 @@
+// tc_gemm.cu -- tcgen05 tensor-core GEMM / implicit-GEMM convolution for sm_100a.
+//
+// One kernel serves every dense contraction of the VAE encoder, the UNet and the ControlNet
+// (rows a7/a8 of SURVEY.md section 8; reference call sites models/guidance/dreammat_guidance.py:
+// 218-229 ControlNetModel.forward, :274-282 UNet2DConditionModel.forward, :290 AutoencoderKL.encode,
+// which run cuDNN/cuBLAS kernels through diffusers):
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T )        fp16 or bf16 operands, fp32 accumulation in TMEM
+//
+//   * linear / 1x1 conv : A = activations [batch, M, K] through a 3-D TMA map
+//   * 3x3 conv (NHWC)   : A is never materialised (no im2col).  The K loop walks (tap, 64-channel
+//                         slab); each step TMA-loads a shifted 4-D box {64 ch, tile_w, tile_h, tile_n}
+//                         of the input, out-of-bounds rows/cols zero-filled by the TMA unit = padding.
+//                         Stride-2 convs use the map's element strides.
+//   * B = weights [N, K] (K-major), K index = tap * Cin + c.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2-5 epilogue (tcgen05.ld -> registers -> fused bias / per-image vector / residual /
+// activation / scale -> 16-byte global stores).  Operand tiles are 128 x 64 (A) and BN x 64 (B)
+// in the 128-byte swizzled K-major layout shared by TMA and the UMMA descriptors; a ring of
+// mbarrier-guarded stages feeds the tensor core, tcgen05.commit releases stages and signals the
+// epilogue.  Two CTAs fit per SM (<= 99 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NTHREADS = 192;
+
+struct GemmParams {
+    int M, N, K;                  // GEMM view; conv: M = n_img*Ho*Wo, K = taps*Cin
+    int batch;                    // grid.z (plain GEMM only)
+    int b_batched;                // B indexed by blockIdx.z as well
+    int is_conv, Cin, taps, kw_n; // kw_n = kernel width (3 or 1)
+    int Ho, Wo, tile_w, tile_h, tile_n;
+    int stride, pad_t, pad_l;
+    // epilogue
+    void* out; int ldc; int64_t out_batch_stride; int out_f32;
+    const void* bias;                       // [N]
+    const void* rowvec; int rows_per_vec; int ld_rowvec;   // [M / rows_per_vec, N]
+    const void* residual; int ld_res; int64_t res_batch_stride;
+    float alpha;                            // applied to the accumulator first
+    float out_scale;                        // applied last
+    int act;                                // 0 none, 1 silu, 2 gelu(erf)
+};
+
+template <typename T> struct Cvt;
+template <> struct Cvt<__half> {
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Cvt<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+template <int BN> struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, typename T>
+__global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y, z = blockIdx.z;
+    const int nk = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            int c_n = 0, c_h = 0, c_w = 0;
+            if (p.is_conv) {
+                int tiles_w = p.Wo / p.tile_w, tiles_h = p.Ho / p.tile_h;
+                int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
+                c_w = tw * p.tile_w * p.stride - p.pad_l;
+                c_h = th * p.tile_h * p.stride - p.pad_t;
+                c_n = tn * p.tile_n;
+            }
+            const int slabs = p.is_conv ? (p.Cin / BK) : nk;
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t b_dst = a_dst + C::A_BYTES;
+                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                if (p.is_conv) {
+                    int tap = kb / slabs, slab = kb - tap * slabs;
+                    int kh = tap / p.kw_n, kw = tap - kh * p.kw_n;
+                    tma_load_4d(a_dst, &tmA, full_bar(stage), slab * BK, c_w + kw, c_h + kh, c_n);
+                } else {
+                    tma_load_3d(a_dst, &tmA, full_bar(stage), kb * BK, m_tile * BM, z);
+                }
+                tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, p.b_batched ? z : 0);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer (one thread)
+            constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
+            constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+                const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + C::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // +32 bytes along K inside the 128-byte swizzle atom = +2 in the (addr >> 4) field
+                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                }
+                umma_commit(empty_bar(stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ---------------------------------------------------- epilogue warps 2..5
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;    // row inside the tile
+        const int64_t m = (int64_t)m_tile * BM + row;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const bool row_ok = m < p.M;
+        const T* bias = (const T*)p.bias;
+        const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
+        const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
+        char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            const int n0 = n_tile * BN + c0;
+            if (!row_ok || n0 >= p.N) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            const bool full = (n0 + 32 <= p.N);
+            if (bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(bias[n0 + j]);
+            }
+            if (rowvec) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(rowvec[n0 + j]);
+            }
+            if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+            } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+            }
+            if (res) {
+                if (full && ((p.ld_res & 7) == 0)) {
+                    const uint4* r4 = reinterpret_cast<const uint4*>(res + n0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u = r4[q];
+                        const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[q * 8 + j] += Cvt<T>::to_f(h[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += Cvt<T>::to_f(res[n0 + j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+            if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(outp) + n0;
+                if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = f[j];
+                }
+            } else {
+                T* o = reinterpret_cast<T*>(outp) + n0;
+                if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        T* h = reinterpret_cast<T*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h[j] = Cvt<T>::from_f(f[q * 8 + j]);
+                        reinterpret_cast<uint4*>(o)[q] = u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = Cvt<T>::from_f(f[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------- host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* m, int bf16, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, const uint32_t* estr) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) { dm_set_error("cuTensorMapEncodeTiled unavailable"); return DM_EDRIVER; }
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dm_set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu,%llu,%llu box=%u,%u,%u,%u", (int)r, rank,
+                     (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                     rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return DM_EDRIVER;
+    }
+    return DM_OK;
+}
+
+template <int BN, typename T>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = tc_gemm_kernel<BN, T>;
+    if (!configured) {
+        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)dm_ceil_div(p.N, BN), (unsigned)dm_ceil_div(p.M, BM), (unsigned)(p.batch > 0 ? p.batch : 1));
+    kern<<<grid, NTHREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st) {
+    if (bf16) {
+        if (bn == 64) return launch<64, __nv_bfloat16>(tmA, tmB, p, st);
+        if (bn == 128) return launch<128, __nv_bfloat16>(tmA, tmB, p, st);
+        if (bn == 256) return launch<256, __nv_bfloat16>(tmA, tmB, p, st);
+    } else {
+        if (bn == 64) return launch<64, __half>(tmA, tmB, p, st);
+        if (bn == 128) return launch<128, __half>(tmA, tmB, p, st);
+        if (bn == 256) return launch<256, __half>(tmA, tmB, p, st);
+    }
+    dm_set_error("unsupported BN %d", bn);
+    return DM_EUNSUPPORTED;
+}
+
+int pick_bn(int N, int bn_hint) {
+    if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
+    if (N <= 64) return 64;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0 && N < 512) return 64;
+    return 128;
+}
+
+void fill_epilogue(GemmParams& p, const dm_epilogue* e, int N) {
+    p.bias = e ? e->bias : nullptr;
+    p.rowvec = e ? e->rowvec : nullptr;
+    p.rows_per_vec = (e && e->rows_per_vec > 0) ? e->rows_per_vec : 1;
+    p.ld_rowvec = (e && e->ld_rowvec > 0) ? e->ld_rowvec : N;
+    p.residual = e ? e->residual : nullptr;
+    p.ld_res = (e && e->ld_res > 0) ? e->ld_res : N;
+    p.res_batch_stride = e ? e->res_batch_stride : 0;
+    p.alpha = e ? e->alpha : 1.0f;
+    p.out_scale = e ? e->out_scale : 1.0f;
+    p.act = e ? e->act : 0;
+    p.out_f32 = e ? e->out_f32 : 0;
+}
+
+}  // namespace
+
+extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
+                       int64_t b_batch_stride, void* C, int64_t ldc, int64_t c_batch_stride, int M, int N, int K,
+                       int batch, const dm_epilogue* ep, int bn_hint, void* stream) {
+    DM_REQUIRE(A && B && C, "null pointer");
+    DM_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "K must be a positive multiple of 64");
+    DM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "row strides must be multiples of 8 elements (16 bytes)");
+    DM_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "16-byte aligned operands");
+    if (batch < 1) batch = 1;
+    int bn = pick_bn(N, bn_hint);
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? a_batch_stride : (int64_t)M * lda) * 2};
+        uint32_t box[3] = {BK, BM, 1}, es[3] = {1, 1, 1};
+        int rc = encode_map(&tmA, bf16, A, 3, dims, str, box, es); if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(b_batch_stride ? batch : 1)};
+        uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(b_batch_stride ? b_batch_stride : (int64_t)N * ldb) * 2};
+        uint32_t box[3] = {BK, (uint32_t)bn, 1}, es[3] = {1, 1, 1};
+        int rc = encode_map(&tmB, bf16, B, 3, dims, str, box, es); if (rc) return rc;
+    }
+    if (batch > 1 && !b_batch_stride) {
+        // B shared across the batch: fold the batch into M (A, C and the residual must be densely stacked)
+        bool dense = a_batch_stride == (int64_t)M * lda && c_batch_stride == (int64_t)M * ldc &&
+                     (!ep || !ep->residual || ep->res_batch_stride == (int64_t)M * (ep->ld_res > 0 ? ep->ld_res : N));
+        if (!dense) { dm_set_error("batched A with shared B requires densely stacked A/C/residual"); return DM_EUNSUPPORTED; }
+        return dm_gemm(bf16, A, lda, 0, B, ldb, 0, C, ldc, 0, M * batch, N, K, 1, ep, bn_hint, stream);
+    }
+    GemmParams p; memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.batch = batch; p.b_batched = (batch > 1) ? 1 : 0; p.is_conv = 0;
+    p.out = C; p.ldc = (int)ldc; p.out_batch_stride = c_batch_stride;
+    fill_epilogue(p, ep, N);
+    return dispatch(tmA, tmB, p, bn, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const void* w, int Cout, int ksize,
+                         int stride, int pad_t, int pad_l, int Ho, int Wo, void* y, int64_t ldc, const dm_epilogue* ep,
+                         int bn_hint, void* stream) {
+    DM_REQUIRE(x && w && y, "null pointer");
+    DM_REQUIRE(Cin % BK == 0, "Cin must be a multiple of 64 (pad the channels)");
+    DM_REQUIRE(ksize == 3 || ksize == 1, "3x3 or 1x1");
+    DM_REQUIRE(stride == 1 || stride == 2, "stride 1 or 2");
+    int tile_w = Wo < BM ? Wo : BM;
+    int tile_h = (BM / tile_w) < Ho ? (BM / tile_w) : Ho;
+    int tile_n = BM / (tile_w * tile_h);
+    DM_REQUIRE(tile_w * tile_h * tile_n == BM && Wo % tile_w == 0 && Ho % tile_h == 0,
+               "output extent must tile into 128-pixel boxes (power-of-two sizes)");
+    int bn = pick_bn(Cout, bn_hint);
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {BK, (uint32_t)(tile_w * stride), (uint32_t)(tile_h * stride), (uint32_t)tile_n};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        int rc = encode_map(&tmA, bf16, x, 4, dims, str, box, es); if (rc) return rc;
+    }
+    int K = ksize * ksize * Cin;
+    {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)Cout, 1};
+        uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * Cout * 2};
+        uint32_t box[3] = {BK, (uint32_t)bn, 1}, es[3] = {1, 1, 1};
+        int rc = encode_map(&tmB, bf16, w, 3, dims, str, box, es); if (rc) return rc;
+    }
+    GemmParams p; memset(&p, 0, sizeof(p));
+    p.M = n_img * Ho * Wo; p.N = Cout; p.K = K; p.batch = 1; p.is_conv = 1; p.Cin = Cin; p.taps = ksize * ksize; p.kw_n = ksize;
+    p.Ho = Ho; p.Wo = Wo; p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+    p.out = y; p.ldc = (int)ldc; p.out_batch_stride = 0;
+    fill_epilogue(p, ep, Cout);
+    return dispatch(tmA, tmB, p, bn, bf16, (cudaStream_t)stream);
+}

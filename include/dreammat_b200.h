@@ -153,6 +153,36 @@ int dm_sds_grad(const float* eps_pred, const float* noise, const float* w, int B
                 float c_uncond, float c_null, float c_noise, float* grad, float* dlatents, float* norms,
                 void* stream);
 
+/* ------------------------------------------------------------------ dense path (a7, a8)
+ * Tensor-core (tcgen05 + TMA + TMEM) contraction used for every conv / linear of the VAE encoder,
+ * UNet and ControlNet: replaces the cuDNN / cuBLAS kernels diffusers dispatches from
+ * models/guidance/dreammat_guidance.py:218-229, :274-282, :290.  fp16 (bf16=0) or bf16 operands,
+ * fp32 accumulation.  Epilogue order: acc*alpha + bias + rowvec -> act -> + residual -> * out_scale. */
+typedef struct {
+    const void* bias;          /* [N] or NULL */
+    const void* rowvec;        /* [M / rows_per_vec, N] (per-image vector, e.g. time embedding) or NULL */
+    int32_t rows_per_vec;
+    int32_t ld_rowvec;
+    const void* residual;      /* [M, ld_res] or NULL */
+    int32_t ld_res;
+    int64_t res_batch_stride;
+    float alpha;
+    float out_scale;
+    int32_t act;               /* 0 none, 1 SiLU, 2 GELU(erf) */
+    int32_t out_f32;           /* 1: C is float32 */
+} dm_epilogue;
+
+/* C[b] = epi(A[b] . B[b]^T): A [M,K] row stride lda, B [N,K] row stride ldb (K-major both), K % 64 == 0.
+ * b_batch_stride == 0 shares B across the batch. */
+int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
+            int64_t b_batch_stride, void* C, int64_t ldc, int64_t c_batch_stride, int M, int N, int K, int batch,
+            const dm_epilogue* ep, int bn_hint, void* stream);
+/* NHWC implicit-GEMM convolution: x [n,H,W,Cin] (Cin % 64 == 0), w [Cout, k*k*Cin] (tap-major, channel
+ * minor), y [n,Ho,Wo,ldc]; zero padding pad_t/pad_l at the top/left, implicit at the bottom/right. */
+int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const void* w, int Cout, int ksize,
+              int stride, int pad_t, int pad_l, int Ho, int Wo, void* y, int64_t ldc, const dm_epilogue* ep,
+              int bn_hint, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
