@@ -64,6 +64,24 @@ SIGNATURES = {
     "dm_sds_grad": (C.c_int, [P, P, P, C.c_int, I64, F, F, F, F, P, P, P, P]),
     "dm_gemm": (C.c_int, [C.c_int, P, I64, I64, P, I64, I64, P, I64, I64, C.c_int, C.c_int, C.c_int, C.c_int, P,
                           C.c_int, P]),
+    "dm_groupnorm": (C.c_int, [C.c_int, P] + [C.c_int] * 5 + [P, P, F, C.c_int, P, C.c_int, P, P]),
+    "dm_groupnorm_bwd": (C.c_int, [C.c_int, P, P] + [C.c_int] * 4 + [P, P, F, C.c_int, P, P, P, P, P]),
+    "dm_layernorm": (C.c_int, [C.c_int, P, I64, C.c_int, P, P, F, P, P]),
+    "dm_geglu": (C.c_int, [C.c_int, P, I64, C.c_int, P, P]),
+    "dm_upsample2x": (C.c_int, [C.c_int, P] + [C.c_int] * 5 + [P, P]),
+    "dm_axpby2d": (C.c_int, [C.c_int, P, I64, F, P, I64, F, I64, C.c_int, P, I64, P]),
+    "dm_transpose": (C.c_int, [C.c_int, P, C.c_int, C.c_int, C.c_int, I64, I64, P, I64, I64, P]),
+    "dm_softmax_rows": (C.c_int, [C.c_int, P, I64, C.c_int, I64, F, P, P]),
+    "dm_softmax_bwd": (C.c_int, [C.c_int, P, P, I64, C.c_int, I64, F, P, P]),
+    "dm_pad_convert": (C.c_int, [C.c_int, P, I64, C.c_int, C.c_int, F, F, P, P]),
+    "dm_unpad_convert": (C.c_int, [C.c_int, P, I64, C.c_int, C.c_int, F, P, P]),
+    "dm_nhwc_to_nchw_f32": (C.c_int, [C.c_int, P] + [C.c_int] * 4 + [P, P]),
+    "dm_vae_sample": (C.c_int, [C.c_int, P, C.c_int, C.c_int, C.c_int, P, F, P, P]),
+    "dm_vae_sample_bwd": (C.c_int, [C.c_int, P, C.c_int, C.c_int, C.c_int, P, F, P, P, P]),
+    "dm_add_noise": (C.c_int, [C.c_int, P, P, P, P] + [C.c_int] * 4 + [P, P]),
+    "dm_timestep_embedding": (C.c_int, [C.c_int, P, C.c_int, C.c_int, P, P]),
+    "dm_silu": (C.c_int, [C.c_int, P, I64, P, P]),
+    "dm_attention": (C.c_int, [C.c_int, P, I64, I64, P, P, I64, I64, P, I64, I64] + [C.c_int] * 5 + [F, P]),
     "dm_conv2d": (C.c_int, [C.c_int, P] + [C.c_int] * 4 + [P] + [C.c_int] * 7 + [P, I64, P, C.c_int, P]),
 }
 

@@ -1,0 +1,602 @@
+// dense_misc.cu -- the non-GEMM kernels of the VAE-encoder / UNet / ControlNet path (rows a7, a8):
+// GroupNorm(+SiLU) forward/backward, LayerNorm, GEGLU, nearest 2x upsample, strided copies,
+// transposes, row softmax forward/backward, layout / dtype conversion at the fp32 boundaries,
+// posterior sampling, add_noise and the sinusoidal timestep embedding.
+// NHWC activations, fp16 or bf16 storage, fp32 math.  All are HBM-bound streaming kernels:
+// 16-byte vector accesses, grid sized in multiples of the SM count for the strided loops.
+//
+// Reference call sites (diffusers modules reached from models/guidance/dreammat_guidance.py:218-292):
+// torch.nn.GroupNorm/SiLU in ResnetBlock2D, LayerNorm + GEGLU in BasicTransformerBlock,
+// Upsample2D (nearest), AutoencoderKL DiagonalGaussianDistribution.sample (:291),
+// DDIMScheduler.add_noise (:463), Timesteps / get_timestep_embedding.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+template <typename T> struct H;
+template <> struct H<__half> {
+    static __device__ __forceinline__ float f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half t(float v) { return __float2half_rn(v); }
+};
+template <> struct H<__nv_bfloat16> {
+    static __device__ __forceinline__ float f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 t(float v) { return __float2bfloat16_rn(v); }
+};
+
+#define DM_DISPATCH_T(bf16, ...)                                  \
+    do {                                                          \
+        if (bf16) { using T = __nv_bfloat16; __VA_ARGS__; }       \
+        else { using T = __half; __VA_ARGS__; }                   \
+    } while (0)
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) {
+    float s = 1.0f / (1.0f + __expf(-x));
+    return s * (1.0f + x * (1.0f - s));
+}
+
+// ----------------------------------------------------------------------------------- GroupNorm
+// stats[(img*G + g)*2 + {0,1}] += (sum, sumsq) over the group's channels and the pixel chunk.
+// One thread owns one channel PAIR (cpg is even for every SD layer) and strides over pixels.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int G,
+                                                       int chunks, float* __restrict__ stats) {
+    extern __shared__ float s_acc[];  // [G*2]
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int pairs = C / 2, cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int px_per_chunk = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
+    const int lanes = max(1, (int)blockDim.x / pairs);   // pixel lanes when pairs < blockDim
+    for (int pr = threadIdx.x % max(pairs, 1); pr < pairs; pr += blockDim.x) {
+        int q = (pairs < (int)blockDim.x) ? threadIdx.x / pairs : 0;
+        if (pairs < (int)blockDim.x && q >= lanes) break;
+        float s = 0.f, ss = 0.f;
+        const T* base = x + ((int64_t)img * HW) * ld + 2 * pr;
+        for (int p = p0 + q; p < p1; p += lanes) {
+            const T* px = base + (int64_t)p * ld;
+            float a = H<T>::f(px[0]), b = H<T>::f(px[1]);
+            s += a + b; ss += a * a + b * b;
+        }
+        int g = (2 * pr) / cpg;
+        atomicAdd(&s_acc[2 * g], s); atomicAdd(&s_acc[2 * g + 1], ss);
+        if (pairs >= (int)blockDim.x) continue; else break;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + ((int64_t)img * G) * 2 + i, s_acc[i]);
+}
+
+// y = act((x - mean) * rstd * gamma + beta), 8 channels (16 B) per thread
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int64_t n_vec, int HW, int C, int ld,
+                                                       int ldy, int G, const float* __restrict__ stats,
+                                                       const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                       float eps, int silu, T* __restrict__ y) {
+    const int vec_per_px = C / 8, cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t px = i / vec_per_px; int c0 = (int)(i - px * vec_per_px) * 8;
+        int img = (int)(px / HW);
+        uint4 u = *reinterpret_cast<const uint4*>(x + px * ld + c0);
+        const T* h = reinterpret_cast<const T*>(&u);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            int g = (c0 + j) / cpg;
+            float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
+            float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float v = (H<T>::f(h[j + k]) - mean) * rstd * H<T>::f(gamma[c0 + j + k]) + H<T>::f(beta[c0 + j + k]);
+                if (silu) v = silu_f(v);
+                oh[j + k] = H<T>::t(v);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + px * ldy + c0) = o;
+    }
+}
+
+// backward pass 1: bstats[(img*G+g)*2] += sum(gamma*dy'), += sum(gamma*dy'*xhat), dy' = dz * act'(y)
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dz, int HW,
+                                                           int C, int G, int chunks, const float* __restrict__ stats,
+                                                           const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                           float eps, int silu, float* __restrict__ bstats) {
+    extern __shared__ float s_acc[];
+    const int img = blockIdx.y, chunk = blockIdx.x, cpg = C / G, pairs = C / 2;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    const int px_per_chunk = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
+    const int lanes = max(1, (int)blockDim.x / pairs);
+    for (int pr = threadIdx.x % pairs; pr < pairs; pr += blockDim.x) {
+        int q = (pairs < (int)blockDim.x) ? threadIdx.x / pairs : 0;
+        if (pairs < (int)blockDim.x && q >= lanes) break;
+        int g = (2 * pr) / cpg;
+        float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
+        float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+        float g0 = H<T>::f(gamma[2 * pr]), g1 = H<T>::f(gamma[2 * pr + 1]);
+        float b0 = H<T>::f(beta[2 * pr]), b1 = H<T>::f(beta[2 * pr + 1]);
+        float a1 = 0.f, a2 = 0.f;
+        for (int p = p0 + q; p < p1; p += lanes) {
+            int64_t off = ((int64_t)img * HW + p) * C + 2 * pr;
+            float xh0 = (H<T>::f(x[off]) - mean) * rstd, xh1 = (H<T>::f(x[off + 1]) - mean) * rstd;
+            float d0 = H<T>::f(dz[off]), d1 = H<T>::f(dz[off + 1]);
+            if (silu) { d0 *= silu_grad(xh0 * g0 + b0); d1 *= silu_grad(xh1 * g1 + b1); }
+            a1 += g0 * d0 + g1 * d1;
+            a2 += g0 * d0 * xh0 + g1 * d1 * xh1;
+        }
+        atomicAdd(&s_acc[2 * g], a1); atomicAdd(&s_acc[2 * g + 1], a2);
+        if (pairs >= (int)blockDim.x) continue; else break;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(bstats + ((int64_t)img * G) * 2 + i, s_acc[i]);
+}
+
+// backward pass 2: dx = rstd * (gamma*dy' - (S1 + xhat*S2)/cnt)  (+ dx_add if given)
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dz,
+                                                           int64_t n_vec, int HW, int C, int G,
+                                                           const float* __restrict__ stats,
+                                                           const float* __restrict__ bstats,
+                                                           const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                           float eps, int silu, const T* __restrict__ dx_add,
+                                                           T* __restrict__ dx) {
+    const int vec_per_px = C / 8, cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t px = i / vec_per_px; int c0 = (int)(i - px * vec_per_px) * 8;
+        int img = (int)(px / HW);
+        uint4 ux = *reinterpret_cast<const uint4*>(x + px * C + c0);
+        uint4 ud = *reinterpret_cast<const uint4*>(dz + px * C + c0);
+        uint4 ua = make_uint4(0, 0, 0, 0);
+        if (dx_add) ua = *reinterpret_cast<const uint4*>(dx_add + px * C + c0);
+        const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
+        const T* ha = reinterpret_cast<const T*>(&ua);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            int g = (c0 + j) / cpg;
+            int64_t si = ((int64_t)img * G + g) * 2;
+            float s = stats[si], ss = stats[si + 1];
+            float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+            float S1 = bstats[si] * inv_cnt, S2 = bstats[si + 1] * inv_cnt;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float gm = H<T>::f(gamma[c0 + j + k]), bt = H<T>::f(beta[c0 + j + k]);
+                float xh = (H<T>::f(hx[j + k]) - mean) * rstd;
+                float d = H<T>::f(hd[j + k]);
+                if (silu) d *= silu_grad(xh * gm + bt);
+                float v = rstd * (gm * d - S1 - xh * S2);
+                if (dx_add) v += H<T>::f(ha[j + k]);
+                oh[j + k] = H<T>::t(v);
+            }
+        }
+        *reinterpret_cast<uint4*>(dx + px * C + c0) = o;
+    }
+}
+
+// ----------------------------------------------------------------------------------- LayerNorm (warp per row)
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, int64_t M, int C,
+                                                        const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                        float eps, T* __restrict__ y) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const T* xr = x + row * C;
+    float vals[40];  // C <= 1280 -> 40 per lane
+    int cnt = 0; float s = 0.f;
+    for (int c = lane; c < C; c += 32) { float v = H<T>::f(xr[c]); vals[cnt++] = v; s += v; }
+    s = warp_sum(s);
+    float mean = s / (float)C, ss = 0.f;
+    for (int k = 0; k < cnt; ++k) { float d = vals[k] - mean; ss += d * d; }
+    ss = warp_sum(ss);
+    float rstd = rsqrtf(ss / (float)C + eps);
+    cnt = 0;
+    for (int c = lane; c < C; c += 32) y[row * C + c] = H<T>::t((vals[cnt++] - mean) * rstd * H<T>::f(gamma[c]) + H<T>::f(beta[c]));
+}
+
+// GEGLU: out[m, j] = h[m, j] * gelu(h[m, D + j])   (diffusers GEGLU: hidden, gate = chunk(2); hidden * gelu(gate))
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, int64_t M, int D, T* __restrict__ out) {
+    int64_t n = M * (int64_t)(D / 8);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t m = i / (D / 8); int j = (int)(i - m * (D / 8)) * 8;
+        uint4 a = *reinterpret_cast<const uint4*>(h + m * 2 * D + j), g = *reinterpret_cast<const uint4*>(h + m * 2 * D + D + j);
+        const T* ha = reinterpret_cast<const T*>(&a); const T* hg = reinterpret_cast<const T*>(&g);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float gv = H<T>::f(hg[k]);
+            oh[k] = H<T>::t(H<T>::f(ha[k]) * (0.5f * gv * (1.0f + erff(gv * 0.70710678118654752f))));
+        }
+        *reinterpret_cast<uint4*>(out + m * D + j) = o;
+    }
+}
+
+// nearest-neighbour 2x upsample, NHWC
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ x, int n, int Hh, int W, int C,
+                                                         T* __restrict__ y) {
+    int64_t nv = (int64_t)n * 2 * Hh * 2 * W * (C / 8);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % (C / 8)); int64_t r = i / (C / 8);
+        int xo = (int)(r % (2 * W)); r /= 2 * W; int yo = (int)(r % (2 * Hh)); int img = (int)(r / (2 * Hh));
+        const uint4* src = reinterpret_cast<const uint4*>(x + (((int64_t)img * Hh + yo / 2) * W + xo / 2) * C) + c;
+        reinterpret_cast<uint4*>(y)[i] = *src;
+    }
+}
+
+// zero-insertion 2x (transpose of a stride-2 gather): y[2i,2j] = x[i,j], else 0
+template <typename T>
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const T* __restrict__ x, int n, int Hh, int W, int C,
+                                                            T* __restrict__ y) {
+    int64_t nv = (int64_t)n * 2 * Hh * 2 * W * (C / 8);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % (C / 8)); int64_t r = i / (C / 8);
+        int xo = (int)(r % (2 * W)); r /= 2 * W; int yo = (int)(r % (2 * Hh)); int img = (int)(r / (2 * Hh));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (((xo | yo) & 1) == 0) v = reinterpret_cast<const uint4*>(x + (((int64_t)img * Hh + yo / 2) * W + xo / 2) * C)[c];
+        reinterpret_cast<uint4*>(y)[i] = v;
+    }
+}
+
+// dst[r, 0:cols] = a*src[r, 0:cols] (+ b*src2[r,0:cols]) with independent row strides (16-byte vectors)
+template <typename T>
+__global__ void __launch_bounds__(256) axpby2d_kernel(const T* __restrict__ s1, int64_t ld1, float a,
+                                                      const T* __restrict__ s2, int64_t ld2, float b, int64_t rows,
+                                                      int cols, T* __restrict__ dst, int64_t ldd) {
+    int vpr = cols / 8;
+    int64_t nv = rows * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr; int c = (int)(i - r * vpr) * 8;
+        uint4 u = *reinterpret_cast<const uint4*>(s1 + r * ld1 + c);
+        if (!s2 && a == 1.0f) { *reinterpret_cast<uint4*>(dst + r * ldd + c) = u; continue; }
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (s2) w = *reinterpret_cast<const uint4*>(s2 + r * ld2 + c);
+        const T* hu = reinterpret_cast<const T*>(&u); const T* hw = reinterpret_cast<const T*>(&w);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) oh[k] = H<T>::t(a * H<T>::f(hu[k]) + (s2 ? b * H<T>::f(hw[k]) : 0.f));
+        *reinterpret_cast<uint4*>(dst + r * ldd + c) = o;
+    }
+}
+
+// batched transpose [B, R, C] -> [B, C, R] through a 32x33 shared tile
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ x, int R, int C, int64_t ldx,
+                                                        int64_t bsx, T* __restrict__ y, int64_t ldy, int64_t bsy) {
+    __shared__ T tile[32][33];
+    const T* xb = x + (int64_t)blockIdx.z * bsx; T* yb = y + (int64_t)blockIdx.z * bsy;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) { int r = r0 + j, c = c0 + tx; if (r < R && c < C) tile[j][tx] = xb[(int64_t)r * ldx + c]; }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) { int c = c0 + j, r = r0 + tx; if (r < R && c < C) yb[(int64_t)c * ldy + r] = tile[tx][j]; }
+}
+
+// row softmax: y = softmax(scale * x) over `cols`; one block per row
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const T* __restrict__ x, int cols, int64_t ld, float scale,
+                                                           T* __restrict__ y) {
+    __shared__ float red[8];
+    const T* xr = x + (int64_t)blockIdx.x * ld; T* yr = y + (int64_t)blockIdx.x * ld;
+    float mx = -3e38f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, H<T>::f(xr[c]) * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mx = fmaxf(mx, red[k]);
+    __syncthreads();
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s += __expf(H<T>::f(xr[c]) * scale - mx);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+    float inv = 1.0f / s;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) yr[c] = H<T>::t(__expf(H<T>::f(xr[c]) * scale - mx) * inv);
+}
+
+// dS = scale * P * (dP - rowsum(P * dP))
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ P, const T* __restrict__ dP, int cols,
+                                                          int64_t ld, float scale, T* __restrict__ dS) {
+    __shared__ float red[8];
+    const T* pr = P + (int64_t)blockIdx.x * ld; const T* dr = dP + (int64_t)blockIdx.x * ld; T* o = dS + (int64_t)blockIdx.x * ld;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s += H<T>::f(pr[c]) * H<T>::f(dr[c]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) o[c] = H<T>::t(scale * H<T>::f(pr[c]) * (H<T>::f(dr[c]) - s));
+}
+
+// fp32 [rows, cin] -> T [rows, cpad]: y = x*scale + shift on the real channels, 0 on the padding
+template <typename T>
+__global__ void __launch_bounds__(256) pad_convert_kernel(const float* __restrict__ x, int64_t rows, int cin, int cpad,
+                                                          float scale, float shift, T* __restrict__ y) {
+    int64_t n = rows * cpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cpad; int c = (int)(i - r * cpad);
+        y[i] = H<T>::t(c < cin ? x[r * cin + c] * scale + shift : 0.f);
+    }
+}
+// T [rows, ld] (first cout channels) -> fp32 [rows, cout] * scale
+template <typename T>
+__global__ void __launch_bounds__(256) unpad_convert_kernel(const T* __restrict__ x, int64_t rows, int ld, int cout,
+                                                            float scale, float* __restrict__ y) {
+    int64_t n = rows * cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cout; int c = (int)(i - r * cout);
+        y[i] = H<T>::f(x[r * ld + c]) * scale;
+    }
+}
+// NHWC T [n, HW, ld] (first C channels) -> NCHW fp32 [n, C, HW]
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restrict__ x, int n, int HW, int ld, int Cc,
+                                                               float* __restrict__ y) {
+    int64_t tot = (int64_t)n * Cc * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW); int64_t r = i / HW; int c = (int)(r % Cc); int img = (int)(r / Cc);
+        y[i] = H<T>::f(x[((int64_t)img * HW + p) * ld + c]);
+    }
+}
+
+// posterior sample (DiagonalGaussianDistribution): z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps) * sf
+// moments NHWC [n, HW, ld] (mean = ch 0..3, logvar = ch 4..7); z, eps NCHW fp32 [n,4,HW]
+template <typename T>
+__global__ void __launch_bounds__(256) vae_sample_kernel(const T* __restrict__ mom, int n, int HW, int ld,
+                                                         const float* __restrict__ eps, float sf, float* __restrict__ z) {
+    int64_t tot = (int64_t)n * 4 * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW); int64_t r = i / HW; int c = (int)(r % 4); int img = (int)(r / 4);
+        const T* m = mom + ((int64_t)img * HW + p) * ld;
+        float mean = H<T>::f(m[c]), lv = fminf(fmaxf(H<T>::f(m[4 + c]), -30.f), 20.f);
+        // diffusers computes the sample in the weights dtype: round the pre-scale sample to T
+        float smp = H<T>::f(H<T>::t(mean + H<T>::f(H<T>::t(__expf(0.5f * lv))) * H<T>::f(H<T>::t(eps[i]))));
+        z[i] = H<T>::f(H<T>::t(smp * sf));
+    }
+}
+// backward: dmom[.., c] = dz*sf ; dmom[.., 4+c] = dz*sf*eps*0.5*std (0 outside the clamp); padding channels 0
+template <typename T>
+__global__ void __launch_bounds__(256) vae_sample_bwd_kernel(const T* __restrict__ mom, int n, int HW, int ld,
+                                                             const float* __restrict__ eps, float sf,
+                                                             const float* __restrict__ dz, T* __restrict__ dmom) {
+    int64_t tot = (int64_t)n * HW * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        int ch = (int)(i % ld); int64_t r = i / ld; int p = (int)(r % HW); int img = (int)(r / HW);
+        float v = 0.f;
+        if (ch < 4) v = dz[((int64_t)img * 4 + ch) * HW + p] * sf;
+        else if (ch < 8) {
+            int c = ch - 4;
+            float lvr = H<T>::f(mom[i]);
+            if (lvr >= -30.f && lvr <= 20.f) {
+                float sd = __expf(0.5f * lvr);
+                int64_t zi = ((int64_t)img * 4 + c) * HW + p;
+                v = dz[zi] * sf * eps[zi] * 0.5f * sd;
+            }
+        }
+        dmom[i] = H<T>::t(v);
+    }
+}
+
+// add_noise + CFG replication: out[(k*B + b), p, 0:4] = sqrt(ac[t_b]) z + sqrt(1-ac[t_b]) noise, k = 0..rep-1; pad 0
+template <typename T>
+__global__ void __launch_bounds__(256) add_noise_kernel(const float* __restrict__ z, const float* __restrict__ noise,
+                                                        const float* __restrict__ sqrt_ac,
+                                                        const float* __restrict__ sqrt_1mac, int B, int HW, int cpad,
+                                                        int rep, T* __restrict__ out) {
+    int64_t tot = (int64_t)rep * B * HW * cpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cpad); int64_t r = i / cpad; int p = (int)(r % HW); int bk = (int)(r / HW); int b = bk % B;
+        float v = 0.f;
+        if (c < 4) { int64_t zi = ((int64_t)b * 4 + c) * HW + p; v = sqrt_ac[b] * z[zi] + sqrt_1mac[b] * noise[zi]; }
+        out[i] = H<T>::t(v);
+    }
+}
+
+// get_timestep_embedding(t, dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_k) | sin(t f_k)]
+template <typename T>
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int n, int dim, T* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int half = dim / 2;
+    if (i >= n * half) return;
+    int b = i / half, k = i % half;
+    float f = expf(-9.210340371976184f * (float)k / (float)half);
+    float a = t[b] * f;
+    out[b * dim + k] = H<T>::t(cosf(a));
+    out[b * dim + half + k] = H<T>::t(sinf(a));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) silu_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = H<T>::t(silu_f(H<T>::f(x[i])));
+}
+
+inline int grid_for(int64_t work, int threads = 256) {
+    int64_t b = dm_ceil_div(work, threads);
+    int64_t cap = (int64_t)DM_NUM_SMS * 8;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+inline int gn_chunks(int n_img, int HW) {
+    int c = (DM_NUM_SMS * 4) / (n_img > 0 ? n_img : 1);
+    if (c < 1) c = 1;
+    int maxc = HW / 64; if (maxc < 1) maxc = 1;
+    return c < maxc ? c : maxc;
+}
+
+}  // namespace
+
+extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, int ld, int G, const void* gamma,
+                            const void* beta, float eps, int silu, void* y, int ldy, float* stats, void* stream) {
+    DM_REQUIRE(x && gamma && beta && y && stats, "null pointer");
+    DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0 && ld % 8 == 0 && ldy % 8 == 0, "channel layout");
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n_img * G, st));
+    int chunks = gn_chunks(n_img, HW);
+    int threads = 256;
+    DM_DISPATCH_T(bf16, gn_stats_kernel<T><<<dim3(chunks, n_img), threads, 2 * G * sizeof(float), st>>>((const T*)x, HW, C, ld, G, chunks, stats));
+    DM_CHECK_LAUNCH();
+    int64_t n_vec = (int64_t)n_img * HW * (C / 8);
+    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<grid_for(n_vec), 256, 0, st>>>((const T*)x, n_vec, HW, C, ld, ldy, G, stats, (const T*)gamma,
+                                                                         (const T*)beta, eps, silu, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_img, int HW, int C, int G,
+                                const void* gamma, const void* beta, float eps, int silu, const float* stats,
+                                float* bstats, const void* dx_add, void* dx, void* stream) {
+    DM_REQUIRE(x && dz && gamma && beta && stats && bstats && dx, "null pointer");
+    DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0, "channel layout");
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * n_img * G, st));
+    int chunks = gn_chunks(n_img, HW);
+    DM_DISPATCH_T(bf16, gn_bwd_stats_kernel<T><<<dim3(chunks, n_img), 256, 2 * G * sizeof(float), st>>>(
+                            (const T*)x, (const T*)dz, HW, C, G, chunks, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats));
+    DM_CHECK_LAUNCH();
+    int64_t n_vec = (int64_t)n_img * HW * (C / 8);
+    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<grid_for(n_vec), 256, 0, st>>>((const T*)x, (const T*)dz, n_vec, HW, C, G, stats, bstats,
+                                                                             (const T*)gamma, (const T*)beta, eps, silu,
+                                                                             (const T*)dx_add, (T*)dx));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_layernorm(int bf16, const void* x, int64_t M, int C, const void* gamma, const void* beta, float eps,
+                            void* y, void* stream) {
+    DM_REQUIRE(x && gamma && beta && y, "null pointer");
+    DM_REQUIRE(C <= 1280, "C <= 1280");
+    if (M == 0) return DM_OK;
+    DM_DISPATCH_T(bf16, layernorm_kernel<T><<<(unsigned)dm_ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, (const T*)gamma,
+                                                                                                        (const T*)beta, eps, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_geglu(int bf16, const void* h, int64_t M, int D, void* out, void* stream) {
+    DM_REQUIRE(h && out && D % 8 == 0, "bad args");
+    DM_DISPATCH_T(bf16, geglu_kernel<T><<<grid_for(M * (D / 8)), 256, 0, (cudaStream_t)stream>>>((const T*)h, M, D, (T*)out));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_upsample2x(int bf16, const void* x, int n, int H, int W, int C, int zero_insert, void* y, void* stream) {
+    DM_REQUIRE(x && y && C % 8 == 0, "bad args");
+    int64_t nv = (int64_t)n * 4 * H * W * (C / 8);
+    if (zero_insert) DM_DISPATCH_T(bf16, zero_insert2x_kernel<T><<<grid_for(nv), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, H, W, C, (T*)y));
+    else DM_DISPATCH_T(bf16, upsample2x_kernel<T><<<grid_for(nv), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, H, W, C, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_axpby2d(int bf16, const void* s1, int64_t ld1, float a, const void* s2, int64_t ld2, float b,
+                          int64_t rows, int cols, void* dst, int64_t ldd, void* stream) {
+    DM_REQUIRE(s1 && dst && cols % 8 == 0 && ld1 % 8 == 0 && ldd % 8 == 0 && (!s2 || ld2 % 8 == 0), "bad args");
+    if (rows == 0) return DM_OK;
+    DM_DISPATCH_T(bf16, axpby2d_kernel<T><<<grid_for(rows * (cols / 8)), 256, 0, (cudaStream_t)stream>>>((const T*)s1, ld1, a, (const T*)s2, ld2, b,
+                                                                                                     rows, cols, (T*)dst, ldd));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_transpose(int bf16, const void* x, int batch, int R, int C, int64_t ldx, int64_t bsx, void* y,
+                            int64_t ldy, int64_t bsy, void* stream) {
+    DM_REQUIRE(x && y, "null pointer");
+    dim3 grid((unsigned)dm_ceil_div(C, 32), (unsigned)dm_ceil_div(R, 32), (unsigned)batch);
+    DM_DISPATCH_T(bf16, transpose_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, R, C, ldx, bsx, (T*)y, ldy, bsy));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_softmax_rows(int bf16, const void* x, int64_t rows, int cols, int64_t ld, float scale, void* y,
+                               void* stream) {
+    DM_REQUIRE(x && y, "null pointer");
+    if (rows == 0) return DM_OK;
+    DM_DISPATCH_T(bf16, softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, cols, ld, scale, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_softmax_bwd(int bf16, const void* P, const void* dP, int64_t rows, int cols, int64_t ld, float scale,
+                              void* dS, void* stream) {
+    DM_REQUIRE(P && dP && dS, "null pointer");
+    if (rows == 0) return DM_OK;
+    DM_DISPATCH_T(bf16, softmax_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)P, (const T*)dP, cols, ld, scale, (T*)dS));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, int cpad, float scale, float shift,
+                              void* y, void* stream) {
+    DM_REQUIRE(x && y && cpad >= cin, "bad args");
+    DM_DISPATCH_T(bf16, pad_convert_kernel<T><<<grid_for(rows * cpad), 256, 0, (cudaStream_t)stream>>>(x, rows, cin, cpad, scale, shift, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_unpad_convert(int bf16, const void* x, int64_t rows, int ld, int cout, float scale, float* y,
+                                void* stream) {
+    DM_REQUIRE(x && y && ld >= cout, "bad args");
+    DM_DISPATCH_T(bf16, unpad_convert_kernel<T><<<grid_for(rows * cout), 256, 0, (cudaStream_t)stream>>>((const T*)x, rows, ld, cout, scale, y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_nhwc_to_nchw_f32(int bf16, const void* x, int n, int HW, int ld, int C, float* y, void* stream) {
+    DM_REQUIRE(x && y, "null pointer");
+    DM_DISPATCH_T(bf16, nhwc_to_nchw_f32_kernel<T><<<grid_for((int64_t)n * C * HW), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, HW, ld, C, y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_vae_sample(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling,
+                             float* z, void* stream) {
+    DM_REQUIRE(moments && eps && z && ld >= 8, "bad args");
+    DM_DISPATCH_T(bf16, vae_sample_kernel<T><<<grid_for((int64_t)n * 4 * HW), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps, scaling, z));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_vae_sample_bwd(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling,
+                                 const float* dz, void* dmoments, void* stream) {
+    DM_REQUIRE(moments && eps && dz && dmoments && ld >= 8, "bad args");
+    DM_DISPATCH_T(bf16, vae_sample_bwd_kernel<T><<<grid_for((int64_t)n * HW * ld), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps,
+                                                                                                               scaling, dz, (T*)dmoments));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_add_noise(int bf16, const float* z, const float* noise, const float* sqrt_ac, const float* sqrt_1mac,
+                            int B, int HW, int cpad, int rep, void* out, void* stream) {
+    DM_REQUIRE(z && noise && sqrt_ac && sqrt_1mac && out && cpad >= 4, "bad args");
+    DM_DISPATCH_T(bf16, add_noise_kernel<T><<<grid_for((int64_t)rep * B * HW * cpad), 256, 0, (cudaStream_t)stream>>>(z, noise, sqrt_ac, sqrt_1mac, B, HW,
+                                                                                                                  cpad, rep, (T*)out));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_timestep_embedding(int bf16, const float* t, int n, int dim, void* out, void* stream) {
+    DM_REQUIRE(t && out && dim % 2 == 0, "bad args");
+    DM_DISPATCH_T(bf16, timestep_embed_kernel<T><<<(unsigned)dm_ceil_div((int64_t)n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, n, dim, (T*)out));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_silu(int bf16, const void* x, int64_t n, void* y, void* stream) {
+    DM_REQUIRE(x && y, "null pointer");
+    DM_DISPATCH_T(bf16, silu_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}

@@ -113,3 +113,205 @@ def conv_weight_to_gemm(w_oihw: torch.Tensor, cin_pad: int = 0, cout_pad: int = 
     w = torch.zeros(cout_p, kh, kw, cin_p, dtype=torch.float32, device=w_oihw.device)
     w[:Cout, :, :, :Cin] = w_oihw.float().permute(0, 2, 3, 1)
     return w.reshape(cout_p, kh * kw * cin_p).to(dtype).contiguous()
+
+
+# ----------------------------------------------------------------------------- streaming kernels
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-5, silu=False, out=None, stats=None):
+    """x [n, H, W, C] (channel slice allowed: stride(-2) = ld) -> same shape; returns (y, stats)."""
+    bf = _is_bf16(x)
+    n, Hh, W, Cc = x.shape
+    ld = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == W * ld and x.stride(0) == Hh * W * ld
+    if out is None:
+        out = torch.empty(n, Hh, W, Cc, device=x.device, dtype=x.dtype)
+    if stats is None:
+        stats = torch.empty(n * groups * 2, device=x.device, dtype=torch.float32)
+    check(lib().dm_groupnorm(bf, ptr_any(x), n, Hh * W, Cc, ld, groups, ptr_any(gamma), ptr_any(beta), eps,
+                             1 if silu else 0, ptr_any(out), out.stride(2), ptr_any(stats), stream_ptr()), "dm_groupnorm")
+    return out, stats
+
+
+def groupnorm_bwd(x, dz, gamma, beta, stats, groups=32, eps=1e-5, silu=False, dx_add=None):
+    bf = _is_bf16(x)
+    n, Hh, W, Cc = x.shape
+    assert x.is_contiguous() and dz.is_contiguous()
+    dx = torch.empty_like(x)
+    bstats = torch.empty(n * groups * 2, device=x.device, dtype=torch.float32)
+    check(lib().dm_groupnorm_bwd(bf, ptr_any(x), ptr_any(dz), n, Hh * W, Cc, groups, ptr_any(gamma), ptr_any(beta), eps,
+                                 1 if silu else 0, ptr_any(stats), ptr_any(bstats),
+                                 ptr_any(dx_add) if dx_add is not None else None, ptr_any(dx), stream_ptr()),
+          "dm_groupnorm_bwd")
+    return dx
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    y = torch.empty_like(x)
+    check(lib().dm_layernorm(bf, ptr_any(x), M, Cc, ptr_any(gamma), ptr_any(beta), eps, ptr_any(y), stream_ptr()),
+          "dm_layernorm")
+    return y
+
+
+def geglu(h):
+    bf = _is_bf16(h)
+    assert h.is_contiguous()
+    D = h.shape[-1] // 2
+    M = h.numel() // (2 * D)
+    out = torch.empty(*h.shape[:-1], D, device=h.device, dtype=h.dtype)
+    check(lib().dm_geglu(bf, ptr_any(h), M, D, ptr_any(out), stream_ptr()), "dm_geglu")
+    return out
+
+
+def upsample2x(x, zero_insert=False):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    n, Hh, W, Cc = x.shape
+    y = torch.empty(n, 2 * Hh, 2 * W, Cc, device=x.device, dtype=x.dtype)
+    check(lib().dm_upsample2x(bf, ptr_any(x), n, Hh, W, Cc, 1 if zero_insert else 0, ptr_any(y), stream_ptr()),
+          "dm_upsample2x")
+    return y
+
+
+def axpby(s1, a=1.0, s2=None, b=1.0, out=None):
+    """out[..., :] = a*s1 + b*s2 over 2-D views [rows, cols] with arbitrary row strides (last dim contiguous)."""
+    bf = _is_bf16(s1)
+    cols = s1.shape[-1]
+    rows = s1.numel() // cols
+
+    def ld(t):
+        assert t.stride(-1) == 1
+        return t.stride(-2) if t.dim() > 1 else cols
+    if out is None:
+        out = torch.empty(s1.shape, device=s1.device, dtype=s1.dtype)
+    check(lib().dm_axpby2d(bf, ptr_any(s1), ld(s1), a, ptr_any(s2) if s2 is not None else None,
+                           ld(s2) if s2 is not None else 0, b, rows, cols, ptr_any(out), ld(out), stream_ptr()),
+          "dm_axpby2d")
+    return out
+
+
+def transpose(x):
+    """[B, R, C] -> [B, C, R] (or 2-D)."""
+    bf = _is_bf16(x)
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x.unsqueeze(0)
+    assert x.stride(2) == 1
+    B, R, Cc = x.shape
+    y = torch.empty(B, Cc, R, device=x.device, dtype=x.dtype)
+    check(lib().dm_transpose(bf, ptr_any(x), B, R, Cc, x.stride(1), x.stride(0), ptr_any(y), R, Cc * R, stream_ptr()),
+          "dm_transpose")
+    return y[0] if squeeze else y
+
+
+def softmax_rows(x, scale=1.0):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    cols = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib().dm_softmax_rows(bf, ptr_any(x), x.numel() // cols, cols, cols, scale, ptr_any(y), stream_ptr()),
+          "dm_softmax_rows")
+    return y
+
+
+def softmax_bwd(P, dP, scale=1.0):
+    bf = _is_bf16(P)
+    cols = P.shape[-1]
+    dS = torch.empty_like(P)
+    check(lib().dm_softmax_bwd(bf, ptr_any(P), ptr_any(dP), P.numel() // cols, cols, cols, scale, ptr_any(dS),
+                               stream_ptr()), "dm_softmax_bwd")
+    return dS
+
+
+def pad_convert(x_f32, cpad, scale=1.0, shift=0.0, dtype=torch.float16):
+    x_f32 = x_f32.contiguous()
+    cin = x_f32.shape[-1]
+    rows = x_f32.numel() // cin
+    y = torch.empty(*x_f32.shape[:-1], cpad, device=x_f32.device, dtype=dtype)
+    check(lib().dm_pad_convert(1 if dtype == torch.bfloat16 else 0, ptr_any(x_f32), rows, cin, cpad, scale, shift,
+                               ptr_any(y), stream_ptr()), "dm_pad_convert")
+    return y
+
+
+def unpad_convert(x, cout, scale=1.0):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    ld = x.shape[-1]
+    rows = x.numel() // ld
+    y = torch.empty(*x.shape[:-1], cout, device=x.device, dtype=torch.float32)
+    check(lib().dm_unpad_convert(bf, ptr_any(x), rows, ld, cout, scale, ptr_any(y), stream_ptr()), "dm_unpad_convert")
+    return y
+
+
+def nhwc_to_nchw_f32(x, Cc):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    n, Hh, W, ld = x.shape
+    y = torch.empty(n, Cc, Hh, W, device=x.device, dtype=torch.float32)
+    check(lib().dm_nhwc_to_nchw_f32(bf, ptr_any(x), n, Hh * W, ld, Cc, ptr_any(y), stream_ptr()), "dm_nhwc_to_nchw_f32")
+    return y
+
+
+def vae_sample(moments, eps, scaling=0.18215):
+    bf = _is_bf16(moments)
+    n, Hh, W, ld = moments.shape
+    z = torch.empty(n, 4, Hh, W, device=moments.device, dtype=torch.float32)
+    check(lib().dm_vae_sample(bf, ptr_any(moments), n, Hh * W, ld, ptr_any(eps.contiguous()), scaling, ptr_any(z),
+                              stream_ptr()), "dm_vae_sample")
+    return z
+
+
+def vae_sample_bwd(moments, eps, dz, scaling=0.18215):
+    bf = _is_bf16(moments)
+    n, Hh, W, ld = moments.shape
+    dm = torch.empty_like(moments)
+    check(lib().dm_vae_sample_bwd(bf, ptr_any(moments), n, Hh * W, ld, ptr_any(eps.contiguous()), scaling,
+                                  ptr_any(dz.contiguous()), ptr_any(dm), stream_ptr()), "dm_vae_sample_bwd")
+    return dm
+
+
+def add_noise(z, noise, sqrt_ac, sqrt_1mac, rep=3, cpad=64, dtype=torch.float16):
+    B, _, Hh, W = z.shape
+    out = torch.empty(rep * B, Hh, W, cpad, device=z.device, dtype=dtype)
+    check(lib().dm_add_noise(1 if dtype == torch.bfloat16 else 0, ptr_any(z.contiguous()), ptr_any(noise.contiguous()),
+                             ptr_any(sqrt_ac.contiguous()), ptr_any(sqrt_1mac.contiguous()), B, Hh * W, cpad, rep,
+                             ptr_any(out), stream_ptr()), "dm_add_noise")
+    return out
+
+
+def timestep_embedding(t_f32, dim=320, dtype=torch.float16):
+    n = t_f32.shape[0]
+    out = torch.empty(n, dim, device=t_f32.device, dtype=dtype)
+    check(lib().dm_timestep_embedding(1 if dtype == torch.bfloat16 else 0, ptr_any(t_f32.contiguous()), n, dim,
+                                      ptr_any(out), stream_ptr()), "dm_timestep_embedding")
+    return out
+
+
+def silu(x):
+    bf = _is_bf16(x)
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().dm_silu(bf, ptr_any(x), x.numel(), ptr_any(y), stream_ptr()), "dm_silu")
+    return y
+
+
+def attention(q, k, v, heads, scale=None, out=None):
+    """q [B,Nq,*], k/v [B,Nk,*] token-major views (last dim contiguous, heads*64 wide) -> [B,Nq,heads*64]."""
+    bf = _is_bf16(q)
+    B, Nq, Cq = q.shape
+    Nk = k.shape[1]
+    assert Cq == heads * 64 and k.shape[2] == Cq and v.shape[2] == Cq
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert k.stride(1) == v.stride(1) and k.stride(0) == v.stride(0)
+    if out is None:
+        out = torch.empty(B, Nq, Cq, device=q.device, dtype=q.dtype)
+    if scale is None:
+        scale = 1.0 / 8.0
+    check(lib().dm_attention(bf, ptr_any(q), q.stride(1), q.stride(0), ptr_any(k), ptr_any(v), k.stride(1), k.stride(0),
+                             ptr_any(out), out.stride(1), out.stride(0), B, heads, Nq, Nk, 64, scale, stream_ptr()),
+          "dm_attention")
+    return out

@@ -183,6 +183,53 @@ int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const v
               int stride, int pad_t, int pad_l, int Ho, int Wo, void* y, int64_t ldc, const dm_epilogue* ep,
               int bn_hint, void* stream);
 
+/* ---- streaming kernels of the dense path (NHWC, fp16/bf16 storage selected by `bf16`, fp32 math) ---- */
+/* torch.nn.GroupNorm (+ optional SiLU) as used by diffusers ResnetBlock2D / Transformer2DModel.norm.
+ * x [n_img, HW, ld] (first C channels), y [n_img, HW, ldy]; stats [n_img*G*2] receives (sum, sumsq)
+ * per group and is what dm_groupnorm_bwd needs. */
+int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, int ld, int G, const void* gamma,
+                 const void* beta, float eps, int silu, void* y, int ldy, float* stats, void* stream);
+/* dx = d/dx [ act(GN(x)) ] . dz (+ dx_add); x, dz, dx dense [n_img, HW, C]; bstats scratch [n_img*G*2] */
+int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_img, int HW, int C, int G, const void* gamma,
+                     const void* beta, float eps, int silu, const float* stats, float* bstats, const void* dx_add,
+                     void* dx, void* stream);
+int dm_layernorm(int bf16, const void* x, int64_t M, int C, const void* gamma, const void* beta, float eps, void* y,
+                 void* stream);
+/* out[m,j] = h[m,j] * gelu(h[m,D+j]), h [M,2D] */
+int dm_geglu(int bf16, const void* h, int64_t M, int D, void* out, void* stream);
+/* nearest 2x (zero_insert=0) or zero-insertion 2x (zero_insert=1, adjoint of a stride-2 gather) */
+int dm_upsample2x(int bf16, const void* x, int n, int H, int W, int C, int zero_insert, void* y, void* stream);
+/* dst[r,0:cols] = a*s1[r,0:cols] + b*s2[r,0:cols] (s2 may be NULL) with independent row strides */
+int dm_axpby2d(int bf16, const void* s1, int64_t ld1, float a, const void* s2, int64_t ld2, float b, int64_t rows,
+               int cols, void* dst, int64_t ldd, void* stream);
+int dm_transpose(int bf16, const void* x, int batch, int R, int C, int64_t ldx, int64_t bsx, void* y, int64_t ldy,
+                 int64_t bsy, void* stream);
+int dm_softmax_rows(int bf16, const void* x, int64_t rows, int cols, int64_t ld, float scale, void* y, void* stream);
+int dm_softmax_bwd(int bf16, const void* P, const void* dP, int64_t rows, int cols, int64_t ld, float scale, void* dS,
+                   void* stream);
+/* fp32 [rows,cin] -> T [rows,cpad] (x*scale+shift, zero padding) and back (first cout channels, * scale) */
+int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, int cpad, float scale, float shift, void* y,
+                   void* stream);
+int dm_unpad_convert(int bf16, const void* x, int64_t rows, int ld, int cout, float scale, float* y, void* stream);
+int dm_nhwc_to_nchw_f32(int bf16, const void* x, int n, int HW, int ld, int C, float* y, void* stream);
+/* DiagonalGaussianDistribution.sample() * scaling_factor (dreammat_guidance.py:290-291) and its backward */
+int dm_vae_sample(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling, float* z,
+                  void* stream);
+int dm_vae_sample_bwd(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling,
+                      const float* dz, void* dmoments, void* stream);
+/* scheduler.add_noise + CFG replication (dreammat_guidance.py:463, :407): out [rep*B, HW, cpad] */
+int dm_add_noise(int bf16, const float* z, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, int B,
+                 int HW, int cpad, int rep, void* out, void* stream);
+int dm_timestep_embedding(int bf16, const float* t, int n, int dim, void* out, void* stream);
+int dm_silu(int bf16, const void* x, int64_t n, void* y, void* stream);
+
+/* Fused attention, head_dim 64: O = softmax(scale * Q K^T) V per (batch, head).  Q [batch,Nq,ldq],
+ * K/V [batch,Nk,ldkv], O [batch,Nq,ldo]; head h occupies columns [64h, 64h+64) of every operand.
+ * Replaces SDPA in diffusers' BasicTransformerBlock (self- and cross-attention). */
+int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, const void* v,
+                 int64_t ldkv, int64_t kv_batch_stride, void* out, int64_t ldo, int64_t out_batch_stride, int batch,
+                 int heads, int Nq, int Nk, int head_dim, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
