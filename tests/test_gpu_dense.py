@@ -1,0 +1,205 @@
+"""GPU parity: dense path (VAE encoder fwd+bwd, ControlNet, UNet, CSD gradient) vs the CPU oracle.
+
+The product computes in fp16 storage / fp32 accumulation, exactly the reference's default
+(`half_precision_weights=True`).  The oracle therefore runs with fp16-rounded weights and the
+storage-rounding hook `q = half().float()`; the residual difference is accumulation order and
+fusion boundaries.  Tolerance: relative L2 error <= 5e-3 on network outputs at this precision
+(measured values are printed; the fp32 drift is reported alongside), 1e-3 on the pure fp32 pieces.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import sd as O
+
+pytestmark = pytest.mark.gpu
+
+Q = lambda x: x.half().float()  # noqa: E731
+TOL16 = 5e-3
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def nchw(x_nhwc, c=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    return x if c is None else x[:, :c]
+
+
+@pytest.fixture(scope="module")
+def small():
+    ucfg = O.UNetConfig(block_out_channels=(64, 128, 256, 256), heads=(1, 2, 4, 4), cross_attention_dim=128)
+    vcfg = O.VAEConfig(block_out_channels=(64, 64, 128, 128))
+    wu = O.round_weights(O.random_unet_weights(ucfg, 0))
+    wc = O.round_weights(O.random_controlnet_weights(ucfg, 1))
+    wv = O.round_weights(O.random_vae_weights(vcfg, 2))
+    return ucfg, vcfg, wu, wc, wv
+
+
+def test_gemm_conv_match_torch_fp32():
+    """Numerics of the tensor-core kernel against a plain fp32 reference of the same op (on the GPU)."""
+    import torch.nn.functional as F
+    from dreammat_b200 import dense_ops as D
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(300, 192, device="cuda", generator=g).half()
+    b = torch.randn(200, 192, device="cuda", generator=g).half()
+    bias = torch.randn(200, device="cuda", generator=g).half()
+    out = D.gemm(a, b, bias=bias, act="silu")
+    ref = F.silu(a.float() @ b.float().t() + bias.float())
+    assert rel(out, ref) < 1e-3
+    x = torch.randn(2, 32, 32, 128, device="cuda", generator=g).half()
+    w = (torch.randn(192, 128, 3, 3, device="cuda", generator=g) / 34).half()
+    y = D.conv2d(x, D.conv_weight_to_gemm(w), 3)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1)
+    assert rel(nchw(y), ref) < 1e-3
+    y = D.conv2d(x, D.conv_weight_to_gemm(w), 3, stride=2, pad=(0, 0), out_hw=(16, 16))
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), stride=2)
+    assert rel(nchw(y), ref) < 1e-3
+    with pytest.raises(Exception):
+        D.gemm(a[:, :100].contiguous(), b[:, :100].contiguous())  # K % 64 != 0 must fail loudly
+
+
+def test_attention_matches_torch_fp32():
+    import torch.nn.functional as F
+    from dreammat_b200 import dense_ops as D
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (B, heads, Nq, Nk) in ((2, 5, 1024, 1024), (2, 20, 64, 77), (1, 2, 4096, 4096)):
+        q = torch.randn(B, Nq, heads * 64, device="cuda", generator=g).half()
+        k = torch.randn(B, Nk, heads * 64, device="cuda", generator=g).half()
+        v = torch.randn(B, Nk, heads * 64, device="cuda", generator=g).half()
+        o = D.attention(q, k, v, heads)
+        sp = lambda t, n: t.float().view(B, n, heads, 64).transpose(1, 2)  # noqa: E731
+        ref = F.scaled_dot_product_attention(sp(q, Nq), sp(k, Nk), sp(v, Nk)).transpose(1, 2).reshape(B, Nq, -1)
+        assert rel(o, ref) < 1e-3, (B, heads, Nq, Nk)
+
+
+def test_unet_matches_oracle(small):
+    from dreammat_b200.nets import UNet
+    from dreammat_b200 import dense_ops as D
+    ucfg, _, wu, _, _ = small
+    g = torch.Generator().manual_seed(3)
+    N, hw = 3, 32
+    z = torch.randn(N, 4, hw, hw, generator=g)
+    t = torch.tensor([37, 500, 940])
+    ctx = torch.randn(N, 77, ucfg.cross_attention_dim, generator=g)
+    ref16 = O.unet_forward(wu, ucfg, Q(z), t, Q(ctx), q=Q)
+    ref32 = O.unet_forward(wu, ucfg, Q(z), t, Q(ctx))
+    net = UNet(wu, ucfg)
+    zp = D.pad_convert(z.permute(0, 2, 3, 1).contiguous().cuda(), 64)
+    out = net.forward(zp, t.float().cuda(), ctx.half().cuda())
+    e16, e32 = rel(out, ref16), rel(out, ref32)
+    print(f"\nunet small: rel err vs fp16-emulating oracle {e16:.2e}, vs fp32 oracle {e32:.2e}, "
+          f"oracle16 vs oracle32 {rel(ref16, ref32):.2e}")
+    assert e16 < TOL16
+
+
+def test_controlnet_matches_oracle(small):
+    from dreammat_b200.nets import ControlNet
+    from dreammat_b200 import dense_ops as D
+    ucfg, _, _, wc, _ = small
+    g = torch.Generator().manual_seed(4)
+    B, hw = 2, 16
+    z = torch.randn(3 * B, 4, hw, hw, generator=g)
+    t = torch.tensor([100, 700] * 3)
+    ctx = torch.randn(3 * B, 77, ucfg.cross_attention_dim, generator=g)
+    cond = torch.rand(B, 22, 8 * hw, 8 * hw, generator=g)
+    down_r, mid_r = O.controlnet_forward(wc, ucfg, Q(z), t, Q(ctx), Q(cond), 0.8, q=Q)
+    net = ControlNet(wc, ucfg)
+    zp = D.pad_convert(z.permute(0, 2, 3, 1).contiguous().cuda(), 64)
+    cp = D.pad_convert(cond.permute(0, 2, 3, 1).contiguous().cuda(), 64)
+    down, mid = net.forward(zp, t.float().cuda(), ctx.half().cuda(), cp, 0.8)
+    errs = [rel(nchw(a), b) for a, b in zip(down, down_r)] + [rel(nchw(mid), mid_r)]
+    print("\ncontrolnet small: rel errs", " ".join(f"{e:.1e}" for e in errs))
+    assert len(down) == 12 and max(errs) < TOL16
+
+
+def test_vae_encoder_forward_backward_match_oracle(small):
+    from dreammat_b200.nets import VAEEncoder
+    from dreammat_b200 import dense_ops as D
+    _, vcfg, _, _, wv = small
+    g = torch.Generator().manual_seed(5)
+    B, R = 2, 128
+    rgb = torch.rand(B, R, R, 3, generator=g)
+    eps = torch.randn(B, 4, R // 8, R // 8, generator=g)
+    x = (rgb * 2 - 1).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    mom_r = O.vae_encode_moments(wv, vcfg, Q(x), q=Q)
+    z_r = O.vae_sample(mom_r, eps, vcfg.scaling_factor, Q)
+    dz = torch.randn(z_r.shape, generator=g)
+    # torch casts are differentiable: gradients are rounded to fp16 at the same points as the activations
+    z_r.backward(dz)
+    vae = VAEEncoder(wv, vcfg)
+    xp = D.pad_convert(rgb.cuda(), 64, 2.0, -1.0)
+    tape = []
+    mom = vae.encode_moments(xp, tape)
+    z = D.vae_sample(mom, eps.cuda(), vcfg.scaling_factor)
+    e_m, e_z = rel(nchw(mom, 8), mom_r), rel(z, z_r)
+    dmom = D.vae_sample_bwd(mom, eps.cuda(), dz.cuda(), vcfg.scaling_factor)
+    dx = vae.backward_input(tape, dmom)
+    e_g = rel(nchw(dx, 3), x.grad)
+    print(f"\nvae small: moments {e_m:.2e} latents {e_z:.2e} input-grad {e_g:.2e}")
+    assert e_m < TOL16 and e_z < TOL16 and e_g < 2 * TOL16
+
+
+def test_guidance_step_matches_oracle(small):
+    """Full a7-a9 slice: rgb -> VAE -> add_noise -> ControlNet + UNet x3 -> CSD grad -> loss -> d rgb."""
+    from dreammat_b200.guidance import PromptProcessorOutput, StableDiffusionLightGuidance
+    ucfg, vcfg, wu, wc, wv = small
+    g = torch.Generator().manual_seed(6)
+    B, R = 2, 128
+    Dm = ucfg.cross_attention_dim
+    rgb = torch.rand(B, R, R, 3, generator=g)
+    cond = torch.rand(B, R, R, 22, generator=g)
+    vd = torch.randn(4, 77, Dm, generator=g)
+    uvd = torch.randn(4, 77, Dm, generator=g)
+    null = torch.randn(1, 77, Dm, generator=g)
+    pu = PromptProcessorOutput(vd[:1], uvd[:1], null, vd, uvd)
+    el, az, dist = torch.tensor([10.0, 70.0]), torch.tensor([20.0, -170.0]), torch.tensor([3.5, 3.5])
+    t = torch.tensor([321, 777])
+    noise = torch.randn(B, 4, R // 8, R // 8, generator=g)
+    veps = torch.randn(B, 4, R // 8, R // 8, generator=g)
+    cfg = dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05, uncond_scale=-0.7,
+               null_scale=-0.2, noise_scale=0.0)
+    guid = StableDiffusionLightGuidance(cfg, ucfg, vcfg, wu, wc, wv)
+    # the 512-resize branch is exercised separately; feed latents-sized inputs through encode_images directly
+    rgb_c = rgb.cuda().requires_grad_(True)
+    lat = guid.encode_images(rgb_c, veps.cuda())
+    ctx3 = pu.get_text_embeddings(el, az, dist, True, return_null_text_embeddings=True)
+    grad, dlat, sums = guid.compute_grad_sds(lat, cond.cuda(), ctx3, t.cuda(), noise.cuda())
+    from dreammat_b200.guidance import _SDSLoss
+    loss = _SDSLoss.apply(lat, dlat, sums[0] / B)
+    loss.backward()
+    # oracle
+    rgb_o = rgb.clone().requires_grad_(True)
+    assert pu.direction_index(el, az, dist).tolist() == [1, 3]
+    ctx3_o = Q(ctx3)
+    loss_o, grad_o, z_o = O.guidance_step(wv, wc, wu, ucfg, vcfg, rgb_o, cond, ctx3_o, t, noise, veps,
+                                          scales=(1.05, -0.7, -0.2, 0.0), cond_scale=1.0, q=Q)
+    loss_o.backward()
+    e_z, e_g, e_l, e_r = rel(lat, z_o), rel(grad, grad_o), abs(float(loss) - float(loss_o)) / abs(float(loss_o)), rel(rgb_c.grad, rgb_o.grad)
+    print(f"\nguidance small: latents {e_z:.2e} sds-grad {e_g:.2e} loss {e_l:.2e} d-rgb {e_r:.2e}")
+    assert e_z < TOL16 and e_g < TOL16 and e_l < 2 * TOL16 and e_r < 3 * TOL16
+
+
+@pytest.mark.slow
+def test_unet_full_size_matches_oracle():
+    """SD-2.1-base topology (865.9 M parameters, random init), one view = 3 CFG samples at 64x64 latents."""
+    from dreammat_b200.nets import UNet
+    from dreammat_b200 import dense_ops as D
+    ucfg = O.UNetConfig()
+    wu = O.round_weights(O.random_unet_weights(ucfg, 7))
+    assert sum(v.numel() for v in wu.values()) == 865910724
+    g = torch.Generator().manual_seed(8)
+    z = torch.randn(3, 4, 64, 64, generator=g)
+    t = torch.tensor([250, 250, 250])
+    ctx = torch.randn(3, 77, 1024, generator=g)
+    with torch.no_grad():
+        ref16 = O.unet_forward(wu, ucfg, Q(z), t, Q(ctx), q=Q)
+    net = UNet(wu, ucfg)
+    zp = D.pad_convert(z.permute(0, 2, 3, 1).contiguous().cuda(), 64)
+    out = net.forward(zp, t.float().cuda(), ctx.half().cuda())
+    e = rel(out, ref16)
+    print(f"\nunet full-size: rel err vs fp16-emulating oracle {e:.2e}")
+    assert e < TOL16
