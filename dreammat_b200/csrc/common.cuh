@@ -12,6 +12,7 @@
 #endif
 
 void dm_set_error(const char* fmt, ...);
+void dm_count_launch();
 
 #define DM_CHECK_CUDA(expr)                                                          \
     do {                                                                             \
@@ -24,6 +25,7 @@ void dm_set_error(const char* fmt, ...);
 
 #define DM_CHECK_LAUNCH()                                                            \
     do {                                                                             \
+        dm_count_launch();                                                           \
         cudaError_t _e = cudaGetLastError();                                         \
         if (_e != cudaSuccess) {                                                     \
             dm_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -12,6 +12,10 @@ void dm_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void dm_count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+extern "C" long long dm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char* dm_last_error(void) { return g_err; }
 extern "C" int dm_version(void) { return 100; }
 

@@ -24,7 +24,7 @@ def _ep(bias=None, rowvec=None, rows_per_vec=1, residual=None, ld_res=0, res_bat
     e.bias = bias.data_ptr() if bias is not None else None
     e.rowvec = rowvec.data_ptr() if rowvec is not None else None
     e.rows_per_vec = rows_per_vec
-    e.ld_rowvec = rowvec.shape[-1] if rowvec is not None else 0
+    e.ld_rowvec = (rowvec.stride(-2) if rowvec.dim() > 1 else rowvec.shape[-1]) if rowvec is not None else 0
     e.residual = residual.data_ptr() if residual is not None else None
     e.ld_res = ld_res
     e.res_batch_stride = res_batch_stride

@@ -33,7 +33,7 @@ class _Base:
     def _vec(self, name, pad=0):
         v = self._src[name].float()
         if pad and pad > v.numel():
-            v = torch.cat([v, torch.zeros(pad - v.numel())])
+            v = torch.cat([v, torch.zeros(pad - v.numel(), device=v.device)])
         self.p[name] = v.to(self.dev, self.dt).contiguous()
 
     def _conv(self, name, cin_pad=0, cout_pad=0):

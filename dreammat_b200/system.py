@@ -1,0 +1,391 @@
+"""Host-side mirrors of the reference's geometry / material / renderer / system plugins.
+
+    DreamMatMesh       <-> `dreammat-mesh`        models/geometry/dreammat_mesh.py:89-274
+    DreamMatMaterial   <-> `dreammat-material`    models/materials/dreammat_material.py:346-797
+    RaytraceRender     <-> `raytracing-renderer`  models/renderers/raytracing_renderer.py:86-222
+    DreamMat           <-> `dreammat-system`      systems/dreammat.py:19-86 (+ systems/utils.py:34-53 Adam)
+
+Same Config field names / defaults and the same call signatures and output keys; every tensor op on the
+per-iteration path is a C-ABI kernel launch.  B200-first departures (all result-preserving):
+  * the mesh and the 128 training cameras are fixed, so each view's G-buffer (covered-pixel indices,
+    positions, normals, view directions) is produced once and kept in HBM instead of re-rasterising it
+    every iteration (128 views x ~105 k px x 40 B = 0.5 GB of 180 GB);
+  * `DreamMat.training_step_fused` runs the iteration as an explicit forward/backward kernel sequence with
+    one flat gradient buffer (what the multi-GPU all-reduce and the fused Adam operate on) instead of a
+    torch autograd graph; `forward()` + autograd wrappers remain for API parity.
+The silhouette antialias pass (dr.antialias, raytracing_renderer.py:127,147,199) is not implemented yet:
+comp_rgb differs from the reference on silhouette pixels only (out-of-scope list).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import render_ops as R
+from ._cabi import MaterialCfg, check, lib, ptr, stream_ptr
+from .scene import normalize_mesh, load_obj, vertex_normals
+
+
+class DreamMatMesh:
+    @dataclass
+    class Config:
+        # models/geometry/dreammat_mesh.py:93-121 (+ BaseGeometry radius)
+        radius: float = 1.0
+        n_input_dims: int = 3
+        n_feature_dims: int = 5
+        pos_encoding_config: dict = field(default_factory=lambda: {
+            "otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19,
+            "base_resolution": 16, "per_level_scale": 1.447269237440378})
+        mlp_network_config: dict = field(default_factory=lambda: {
+            "otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64,
+            "n_hidden_layers": 1})
+        shape_init: str = ""
+        shape_init_params: Optional[Any] = None
+        shape_init_mesh_up: str = "+z"
+        shape_init_mesh_front: str = "+x"
+
+    def __init__(self, cfg: Optional[dict] = None, device="cuda", mesh=None, seed: int = 0):
+        self.cfg = self.Config(**(cfg or {}))
+        self.device = torch.device(device)
+        if self.cfg.n_input_dims != 3:
+            raise NotImplementedError("n_input_dims=2 (uv) is not selected by configs/dreammat.yaml")
+        pe = self.cfg.pos_encoding_config
+        self.hg = R.default_hashgrid_cfg(self.cfg.radius, pe["n_levels"], pe["log2_hashmap_size"], pe["base_resolution"],
+                                         pe["per_level_scale"], self.cfg.mlp_network_config["n_neurons"],
+                                         self.cfg.n_feature_dims)
+        n_grid, _ = R.hashgrid_num_params(self.hg)
+        self.n_grid = n_grid
+        enc_dim = pe["n_levels"] * pe["n_features_per_level"]
+        nh = self.cfg.mlp_network_config["n_neurons"]
+        self.n_w1, self.n_w2 = nh * enc_dim, self.cfg.n_feature_dims * nh
+        # ONE flat parameter / gradient / Adam-state buffer: [grid | W1 | W2] (16-byte aligned sub-buffers)
+        self.n_params = n_grid + self.n_w1 + self.n_w2
+        g = torch.Generator().manual_seed(seed)
+        flat = torch.empty(self.n_params)
+        flat[:n_grid] = torch.rand(n_grid, generator=g) * 2e-4 - 1e-4            # tcnn init U(-1e-4, 1e-4)
+        b1, b2 = 1.0 / enc_dim ** 0.5, 1.0 / nh ** 0.5                             # nn.Linear default (kaiming a=sqrt 5)
+        flat[n_grid:n_grid + self.n_w1] = (torch.rand(self.n_w1, generator=g) * 2 - 1) * b1
+        flat[n_grid + self.n_w1:] = (torch.rand(self.n_w2, generator=g) * 2 - 1) * b2
+        self.params = flat.to(self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.grid, self.W1, self.W2 = self._views(self.params)
+        self.dgrid, self.dW1, self.dW2 = self._views(self.grads)
+        if mesh is not None:
+            v, f = mesh
+        elif self.cfg.shape_init.startswith("mesh:"):
+            assert isinstance(self.cfg.shape_init_params, float)
+            vv, ff = load_obj(self.cfg.shape_init[5:])
+            v = torch.from_numpy(normalize_mesh(vv, self.cfg.shape_init_params, self.cfg.shape_init_mesh_up,
+                                                self.cfg.shape_init_mesh_front).astype(np.float32))
+            f = torch.from_numpy(ff.astype(np.int32))
+        else:
+            raise ValueError(f"Unknown shape initialization type: {self.cfg.shape_init}")
+        self.v_pos, self.t_pos_idx = v.float().contiguous(), f.int().contiguous()
+        self.v_nrm = vertex_normals(self.v_pos, self.t_pos_idx)
+
+    def _views(self, flat):
+        g = flat[:self.n_grid]
+        w1 = flat[self.n_grid:self.n_grid + self.n_w1].view(-1, self.hg.n_levels * 2)
+        w2 = flat[self.n_grid + self.n_w1:].view(self.cfg.n_feature_dims, -1)
+        return g, w1, w2
+
+    def isosurface(self):
+        return self
+
+    def forward(self, points: torch.Tensor, output_normal: bool = False) -> Dict[str, torch.Tensor]:
+        """dreammat_mesh.py:239-254 (autograd path; the fused step calls the kernels directly)."""
+        assert output_normal is False, "Normal output is not supported for DreamMatMesh"
+        g = self.grid.detach().requires_grad_(True)
+        return {"features": R.hashgrid_mlp(points.view(-1, 3), g, self.W1, self.W2, self.hg).view(*points.shape[:-1], -1)}
+
+    __call__ = forward
+
+    def state_dict(self):
+        """Keys / shapes of the reference checkpoint."""
+        return {"encoding.encoding.encoding.params": self.grid, "feature_network.layers.0.weight": self.W1,
+                "feature_network.layers.2.weight": self.W2}
+
+
+class DreamMatMaterial:
+    @dataclass
+    class Config:
+        # models/materials/dreammat_material.py:348-366
+        material_activation: str = "sigmoid"
+        environment_texture: str = "load/lights/mud_road_puresky_1k.hdr"
+        environment_scale: float = 1.0
+        min_metallic: float = 0.0
+        max_metallic: float = 0.9
+        min_roughness_squre: float = 0.01
+        max_roughness_squre: float = 0.9
+        min_roughness: float = 0.1
+        max_roughness: float = 0.95
+        use_bump: bool = True
+        diffuse_sample_num: int = 512
+        specular_sample_num: int = 256
+        geometry_type: str = "schlick"
+        random_azimuth: bool = True
+        use_raytracing: bool = True
+
+    def __init__(self, cfg: Optional[dict] = None, device="cuda", env_maps: Optional[List[torch.Tensor]] = None,
+                 fg_lut: Optional[torch.Tensor] = None, envlight: Optional[list] = None):
+        self.cfg = self.Config(**(cfg or {}))
+        self.device = torch.device(device)
+        c = self.cfg
+        if c.material_activation != "sigmoid" or c.geometry_type != "schlick" or not c.random_azimuth:
+            raise NotImplementedError("only the dreammat.yaml material settings are on this path")
+        # self.light[i]: lat-long radiance maps (dreammat_material.py:379-386), stored float4-padded
+        self.light = [R.envmap_pack(m.to(self.device)) for m in (env_maps or [])]
+        self.tab_d = R.direction_tables(c.diffuse_sample_num).to(self.device)
+        self.tab_s = R.direction_tables(c.specular_sample_num).to(self.device)
+        self.mc_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness_squre, c.max_roughness_squre,
+                                  c.diffuse_sample_num, c.specular_sample_num)
+        self.ss_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness, c.max_roughness,
+                                  c.diffuse_sample_num, c.specular_sample_num)
+        self.FG_LUT = fg_lut.to(self.device).contiguous() if fg_lut is not None else None
+        self.envlight = envlight  # [(diffuse_cube, [spec mips])] per env (split-sum branch)
+        self.bvh = None
+
+    def set_raytracer(self, bvh):
+        """dreammat_material.py:426-427; here the tracer is the device BVH handle."""
+        self.bvh = bvh
+
+    def forward(self, pts, features, features_jitter, viewdirs, normals, env_id, rand_d=None, rand_s=None,
+                want_aux=True, reg_weight_n=None, **kwargs):
+        """dreammat_material.py:713-763 -> (outputs dict, mat_reg)."""
+        n = features.shape[0]
+        e = int(env_id)
+        if self.cfg.use_raytracing:
+            if rand_d is None:
+                rand_d = torch.rand(n, device=self.device)           # appendix B #5
+            if rand_s is None:
+                rand_s = torch.rand(n, device=self.device)           # appendix B #6
+            color, reg, aux = R.shade_mc(features, features_jitter, pts, normals, viewdirs, rand_d, rand_s, self.mc_cfg,
+                                         self.bvh, self.light[e], self.tab_d, self.tab_s, want_aux, reg_weight_n)
+        else:
+            dcube, mips = self.envlight[e]
+            color, reg, aux = R.shade_splitsum(features, features_jitter, normals, viewdirs, self.ss_cfg, self.FG_LUT,
+                                               dcube, mips, want_aux, reg_weight_n)
+        out = {"color": color}
+        out.update(aux)
+        return out, reg
+
+    __call__ = forward
+
+
+class RaytraceRender:
+    @dataclass
+    class Config:
+        context_type: str = "gl"   # raytracing_renderer.py:88-90 (kept for config compatibility; unused)
+        radius: float = 1.0
+
+    def __init__(self, cfg: Optional[dict] = None, geometry: DreamMatMesh = None, material: DreamMatMaterial = None,
+                 background=None, device="cuda"):
+        self.cfg = self.Config(**(cfg or {}))
+        self.device = torch.device(device)
+        self.geometry, self.material = geometry, material
+        self.mesh = geometry.isosurface()
+        self.ray_tracer = R.Bvh(self.mesh.v_pos, self.mesh.t_pos_idx)
+        self.material.set_raytracer(self.ray_tracer)
+        self.v_pos_d = self.mesh.v_pos.to(self.device)
+        self.v_nrm_d = self.mesh.v_nrm.to(self.device)
+        self.tris_d = self.mesh.t_pos_idx.to(self.device)
+        self.change_eps = 0.05
+        self._cache: Dict[int, dict] = {}
+
+    def gbuffer(self, rays_o, rays_d, mvp_mtx, w2c, key: Optional[int] = None):
+        """raytracing_renderer.py:122-159 for ONE view; cached under `key` (fixed view id)."""
+        if key is not None and key in self._cache:
+            return self._cache[key]
+        dev = self.device
+        rast, gb_pos, gb_nrm, mask, comp_normal = R.raster_gbuffer(
+            self.ray_tracer, self.v_pos_d, self.v_nrm_d, self.tris_d, rays_o.to(dev), rays_d.to(dev), mvp_mtx.to(dev),
+            w2c.to(dev))
+        pix = R.compact_mask(mask)
+        vd = (-rays_d.to(dev)).reshape(-1, 3).contiguous()
+        g = {"pix": pix, "pn": int(pix.shape[0]), "pts": R.gather_rows(gb_pos.view(-1, 3), pix),
+             "nrm": R.gather_rows(gb_nrm.view(-1, 3), pix), "vd": R.gather_rows(vd, pix),
+             "comp_depth": R.depth_normalize(rast, mask).view(1, *rast.shape[1:3], 1), "comp_normal": comp_normal,
+             "opacity": mask.view(1, *rast.shape[1:3], 1).float()}
+        if key is not None:
+            self._cache[key] = g
+        return g
+
+    def forward(self, env_id, rays_o, rays_d, w2c, mvp_mtx, camera_positions=None, light_positions=None, height=None,
+                width=None, view_id=None, **kwargs) -> Dict[str, Any]:
+        """raytracing_renderer.py:109-222 (per-view loop so that B > 1 is well defined)."""
+        B = mvp_mtx.shape[0]
+        H, W = rays_d.shape[1], rays_d.shape[2]
+        outs: Dict[str, list] = {}
+        regs = []
+        gbs = [self.gbuffer(rays_o[b:b + 1], rays_d[b:b + 1], mvp_mtx[b:b + 1], w2c[b:b + 1],
+                            int(view_id[b]) if view_id is not None else None) for b in range(B)]
+        total = sum(g["pn"] for g in gbs)
+        for b, g in enumerate(gbs):
+            n = g["pn"]
+            ang = torch.rand(n, 1, device=self.device)                               # appendix B #3 (device draw)
+            eps = torch.randn(n, 1, device=self.device) * self.change_eps            # appendix B #4
+            pj = R.jitter_positions(g["pts"], g["nrm"], ang, eps)
+            geo = self.geometry
+            grid = geo.grid if geo.grid.requires_grad else geo.grid.detach().requires_grad_(True)
+            f = R.hashgrid_mlp(g["pts"], grid, geo.W1, geo.W2, geo.hg)
+            fj = R.hashgrid_mlp(pj, grid, geo.W1, geo.W2, geo.hg)
+            so, reg = self.material(g["pts"], f, fj, g["vd"], g["nrm"], env_id[b], reg_weight_n=total)
+            regs.append(reg)
+            canv = {"comp_rgb": R.scatter_canvas(so["color"], g["pix"], H * W).view(1, H, W, 3)}
+            for k_out, k_in, c in (("albedo", "albedo", 3), ("metalness", "metalness", 1), ("roughness", "roughness", 1),
+                                   ("specular_light", "specular_lights", 3), ("diffuse_light", "diffuse_lights", 3),
+                                   ("specular_color", "specular_colors", 3), ("diffuse_color", "diffuse_colors", 3)):
+                canv[k_out] = R.scatter_canvas(so[k_in].detach().view(n, c), g["pix"], H * W).view(1, H, W, c)
+            canv.update(opacity=g["opacity"], comp_depth=g["comp_depth"], comp_normal=g["comp_normal"])
+            for k, v in canv.items():
+                outs.setdefault(k, []).append(v)
+        out = {k: torch.cat(v, 0) for k, v in outs.items()}
+        out["loss_mat_reg"] = torch.stack(regs).sum()
+        return out
+
+    __call__ = forward
+
+
+class DreamMat:
+    """systems/dreammat.py:19-86 + Adam of systems/utils.py:34-53 (lr .01, betas (.9,.99), eps 1e-15)."""
+
+    @dataclass
+    class Config:
+        loss: dict = field(default_factory=lambda: {"lambda_sds": 1.0, "lambda_mat_reg": 1.0})
+        optimizer: dict = field(default_factory=lambda: {"name": "Adam", "args": {"betas": [0.9, 0.99], "eps": 1e-15, "lr": 0.01}})
+
+    def __init__(self, cfg: Optional[dict], geometry: DreamMatMesh, material: DreamMatMaterial, renderer: RaytraceRender,
+                 guidance, prompt_utils, device="cuda"):
+        self.cfg = self.Config(**(cfg or {}))
+        self.geometry, self.material, self.renderer = geometry, material, renderer
+        self.guidance, self.prompt_utils = guidance, prompt_utils
+        self.device = torch.device(device)
+        self.m = torch.zeros_like(geometry.params)
+        self.v = torch.zeros_like(geometry.params)
+        self.global_step = 0
+        self.world_size, self.rank = 1, 0
+
+    def C(self, v):
+        from .guidance import C
+        return C(v, 0, self.global_step)
+
+    def forward(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        return self.renderer(**batch)
+
+    @staticmethod
+    def _event():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _mark(self, name):
+        self._events.append((name, self._event()))
+
+    def section_times(self) -> Dict[str, float]:
+        """CUDA-event split of the LAST training_step_fused (ms): render fwd | VAE fwd | ControlNet+UNet | VAE bwd |
+        shader + hash-grid backward + all-reduce + Adam."""
+        torch.cuda.synchronize()
+        ev = self._events
+        out = {ev[i][0] + "_ms": ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
+        out["dense_ms"] = out.get("vae_fwd_ms", 0) + out.get("unet_cn_ms", 0) + out.get("vae_bwd_ms", 0)
+        out["total_ms"] = ev[0][1].elapsed_time(ev[-1][1])
+        return out
+
+    def profile_step(self, make_batch, V):
+        b, tot = make_batch()
+
+        class _N:
+            def __getitem__(self, i):
+                return None
+        b["rays_o"] = b["rays_d"] = _N()
+        self.training_step_fused(b, global_views=V, total_pn_global=tot)
+        return self.section_times()
+
+    def optimizer_step(self, grad_scale: float = 1.0):
+        a = self.cfg.optimizer["args"]
+        self.global_step += 1
+        R.adam_step(self.geometry.params, self.geometry.grads, self.m, self.v, a["lr"], a["betas"][0], a["betas"][1],
+                    a["eps"], self.global_step, grad_scale)
+
+    def training_step_fused(self, batch: Dict[str, Any], global_views: Optional[int] = None,
+                            total_pn_global: Optional[int] = None, rng: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        """One SDS iteration (systems/dreammat.py:57-86 + backward + Adam) as an explicit kernel sequence.
+
+        batch: output of the data mirror, already on the device (condition_map [B,H,W,22] fp32, cameras, env_id,
+        view_id).  `global_views` / `total_pn_global`: batch-wide normalisers when the views are sharded over
+        ranks (loss_sds is a mean over views, loss_mat_reg a mean over covered pixels of the whole batch)."""
+        geo, mat, ren, guid = self.geometry, self.material, self.renderer, self.guidance
+        guid.update_step(0, self.global_step)
+        lam_sds, lam_reg = self.C(self.cfg.loss["lambda_sds"]), self.C(self.cfg.loss["lambda_mat_reg"])
+        B = batch["mvp_mtx"].shape[0]
+        Bg = global_views or B
+        H, W = batch["height"], batch["width"]
+        dev = self.device
+        st = stream_ptr()
+        self._events = [("start", self._event())]
+        gbs = [ren.gbuffer(batch["rays_o"][b:b + 1], batch["rays_d"][b:b + 1], batch["mvp_mtx"][b:b + 1],
+                           batch["w2c"][b:b + 1], int(batch["view_id"][b])) for b in range(B)]
+        total_pn = total_pn_global or sum(g["pn"] for g in gbs)
+        canvas = torch.empty(B, H * W, 3, device=dev)
+        check(lib().dm_fill(ptr(canvas), canvas.numel(), 1.0, st), "dm_fill")
+        reg_sums = torch.zeros(2, device=dev)
+        saved = []
+        for b, g in enumerate(gbs):
+            n = g["pn"]
+            if rng is not None:   # explicit randomness for parity tests
+                ang, eps, rd, rs = (rng[k][b].to(dev).reshape(-1).contiguous() for k in ("rand_ang", "normal_eps", "rand_d", "rand_s"))
+            else:
+                ang, eps = torch.rand(n, device=dev), torch.randn(n, device=dev) * ren.change_eps
+                rd, rs = torch.rand(n, device=dev), torch.rand(n, device=dev)
+            pj = R.jitter_positions(g["pts"], g["nrm"], ang, eps)
+            f = torch.empty(n, 5, device=dev); fj = torch.empty(n, 5, device=dev)
+            check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(g["pts"]), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(f), st), "hashgrid fwd")
+            check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(pj), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(fj), st), "hashgrid fwd")
+            color = torch.empty(n, 3, device=dev); jac = torch.empty(n, 9, device=dev)
+            env = mat.light[int(batch["env_id"][b])]
+            check(lib().dm_shade_mc_fwd(C.byref(mat.mc_cfg), ren.ray_tracer.h, ptr(env), env.shape[0], env.shape[1],
+                                        ptr(mat.tab_d), ptr(mat.tab_s), ptr(g["pts"]), ptr(g["nrm"]), ptr(g["vd"]), ptr(f),
+                                        ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
+                                        None, st), "dm_shade_mc_fwd")
+            check(lib().dm_scatter_canvas(ptr(color), ptr(g["pix"]), n, 3, ptr(canvas[b]), st), "dm_scatter_canvas")
+            saved.append((g, pj, f, fj, jac))
+        comp_rgb = canvas.view(B, H, W, 3).requires_grad_(True)
+        self._mark("render_fwd")
+        # guidance (dreammat_guidance.py:536-602): VAE encode with grad, ControlNet + UNet x3 under no_grad, CSD gradient
+        from .guidance import _SDSLoss
+        lat = guid.encode_images(comp_rgb, rng["vae_eps"].to(dev) if rng is not None else None)
+        self._mark("vae_fwd")
+        ctx3 = self.prompt_utils.get_text_embeddings(batch["elevation"], batch["azimuth"], batch["camera_distances"],
+                                                     guid.cfg.view_dependent_prompting, return_null_text_embeddings=True)
+        grad, dlat, sums = guid.compute_grad_sds(lat, batch["condition_map"], ctx3, rng["t"].to(dev) if rng is not None else None,
+                                                 rng["noise"].to(dev) if rng is not None else None)
+        self._mark("unet_cn")
+        loss_sds = _SDSLoss.apply(lat, dlat, sums[0] / B) * (B / Bg)          # mean over the GLOBAL batch of views
+        (lam_sds * loss_sds).backward()
+        self._mark("vae_bwd")
+        gout = {"grad_norm": sums[1].sqrt()}
+        dcanvas = comp_rgb.grad.view(B, H * W, 3)
+        # backward into the hash grid / MLP
+        geo.grads.zero_()
+        for b, (g, pj, f, fj, jac) in enumerate(saved):
+            n = g["pn"]
+            dcolor = torch.empty(n, 3, device=dev)
+            check(lib().dm_gather_canvas_grad(ptr(dcanvas[b]), ptr(g["pix"]), n, 3, ptr(dcolor), st), "gather")
+            df = torch.empty(n, 5, device=dev); dfj = torch.empty(n, 5, device=dev)
+            check(lib().dm_shade_bwd(C.byref(mat.mc_cfg), ptr(f), ptr(fj), ptr(dcolor), ptr(jac), lam_reg * 0.25 / total_pn,
+                                     lam_reg * 0.1 / total_pn, n, ptr(df), ptr(dfj), st), "dm_shade_bwd")
+            for pts_, d_ in ((g["pts"], df), (pj, dfj)):
+                check(lib().dm_hashgrid_mlp_bwd(C.byref(geo.hg), ptr(pts_), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(d_),
+                                                ptr(geo.dgrid), ptr(geo.dW1), ptr(geo.dW2), st), "hashgrid bwd")
+        loss_reg = (0.25 * reg_sums[0] + 0.1 * reg_sums[1]) / total_pn
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(geo.grads, op=dist.ReduceOp.SUM)     # the single collective of the step (NVLink / NVSwitch)
+        self.optimizer_step()
+        self._mark("render_bwd_adam")
+        return {"loss": lam_sds * loss_sds.detach() + lam_reg * loss_reg, "loss_sds": loss_sds.detach(),
+                "loss_mat_reg": loss_reg, "comp_rgb": comp_rgb.detach(), "grad_norm": gout["grad_norm"]}

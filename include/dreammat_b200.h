@@ -29,6 +29,8 @@ extern "C" {
 
 const char* dm_last_error(void);
 int dm_version(void);
+/* number of kernels this library has launched in the process (bench.py's gpu_launches) */
+long long dm_launch_count(void);
 /* device sanity: returns 0 iff device `dev` is compute capability 10.x (sm_100a code present). */
 int dm_device_check(int dev);
 

@@ -179,8 +179,16 @@ def test_guidance_step_matches_oracle(small):
                                           scales=(1.05, -0.7, -0.2, 0.0), cond_scale=1.0, q=Q)
     loss_o.backward()
     e_z, e_g, e_l, e_r = rel(lat, z_o), rel(grad, grad_o), abs(float(loss) - float(loss_o)) / abs(float(loss_o)), rel(rgb_c.grad, rgb_o.grad)
-    print(f"\nguidance small: latents {e_z:.2e} sds-grad {e_g:.2e} loss {e_l:.2e} d-rgb {e_r:.2e}")
-    assert e_z < TOL16 and e_g < TOL16 and e_l < 2 * TOL16 and e_r < 3 * TOL16
+    # fp16 noise floor of the CSD combination: the three CFG branches are strongly correlated and their
+    # coefficients nearly cancel (1.05 - 0.7 - 0.2), which amplifies the ~1e-3 storage-rounding error of
+    # each eps by ~|c|+|u|+|n| / |c+u+n| ~ 13x.  Measure that floor with the oracle itself (fp16 emulation
+    # vs pure fp32) and require the kernels to sit within 2x of it.
+    _, grad_32, _ = O.guidance_step(wv, wc, wu, ucfg, vcfg, rgb.clone(), cond, ctx3_o, t, noise, veps,
+                                    scales=(1.05, -0.7, -0.2, 0.0), cond_scale=1.0)
+    floor = rel(grad_o, grad_32)
+    print(f"\nguidance small: latents {e_z:.2e} sds-grad {e_g:.2e} (fp16 floor {floor:.2e}) loss {e_l:.2e} d-rgb {e_r:.2e}")
+    assert e_z < TOL16 and e_l < 2 * TOL16
+    assert e_g < max(2 * floor, TOL16) and e_r < max(3 * floor, 3 * TOL16)
 
 
 @pytest.mark.slow
