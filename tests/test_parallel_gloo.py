@@ -1,0 +1,94 @@
+"""world_size-2 gloo test of the view-parallel step's host logic (no GPU): sharding, the global
+normalisers and the single gradient all-reduce must reproduce the single-process gradient.  The per-view
+compute is the CPU oracle (render half only, with a quadratic stand-in for the SDS term so that the test
+stays in seconds)."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from oracle import render as OR
+from tests._fixtures import make_scene
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _view_grad(sc, b, P, n_grid, meta, env, inv_views, total_pn, target):
+    """d/dP of [ mean-over-views 0.5*||rgb - target||^2 + batch-mean mat_reg ] restricted to view b."""
+    grid, W1, W2 = P[:n_grid], P[n_grid:n_grid + 2048].view(64, 32), P[n_grid + 2048:].view(5, 64)
+    sel = sc["gb"]["selector"][b]
+    pts, nrm, vd = sc["gb"]["gb_pos"][b][sel], sc["gb"]["gb_normal"][b][sel], sc["gb"]["gb_viewdirs"][b][sel]
+    n = pts.shape[0]
+    g = torch.Generator().manual_seed(100 + b)
+    ang, eps = torch.rand(n, 1, generator=g), torch.randn(n, 1, generator=g) * 0.05
+    rd, rs = torch.rand(n, 1, 1, generator=g), torch.rand(n, 1, 1, generator=g)
+    f = OR.geometry_forward(pts, grid, W1, W2, meta)
+    fj = OR.geometry_forward(OR.jitter_positions(pts, nrm, ang, eps), grid, W1, W2, meta)
+    al, me, ro, _ = OR.material_params(f, fj)
+    o = OR.shade_raytracing(pts, nrm, vd, env, me, ro, al, rd, rs, lambda oo, dd: sc["tracer"].trace(oo, dd)[1],
+                            n_diffuse=16, n_specular=8)
+    m, mj = torch.sigmoid(f), torch.sigmoid(fj)
+    kd, ks = (m[:, :3] - mj[:, :3]).abs(), (m[:, 3:5] - mj[:, 3:5]).abs()
+    reg = (0.25 * (kd.mean(-1) * kd[:, 2]).sum() + 0.1 * (ks[:, 0] * ks[:, 1]).sum()) / total_pn
+    loss = 0.5 * ((o["color"] - target) ** 2).sum() * inv_views + reg
+    return loss
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from dreammat_b200.parallel import allreduce_gradients, global_pixel_count, shard_slice
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    V = 4
+    sc = make_scene(res=16, subdiv=2, bump=0.1, seed=0, n_views=V)
+    meta, total = OR.hashgrid_meta(log2_T=10)   # small table: the test is about the sharding algebra
+    n_grid = total * 2
+    g = torch.Generator().manual_seed(0)
+    P0 = torch.cat([(torch.rand(n_grid, generator=g) * 2 - 1) * 0.3, (torch.rand(2048, generator=g) * 2 - 1) / 5.6,
+                    (torch.rand(320, generator=g) * 2 - 1) / 8])
+    env = OR.synthetic_envmap(32, 64, 0)
+    pn = [int(sc["gb"]["selector"][b].sum()) for b in range(V)]
+    view_ids = list(range(V))
+    total_pn = global_pixel_count(pn, view_ids)
+    mine = view_ids[shard_slice(V, rank, world)]
+    P = P0.clone().requires_grad_(True)
+    loss = sum(_view_grad(sc, b, P, n_grid, meta, env, 1.0 / V, total_pn, 0.3) for b in mine)
+    loss.backward()
+    flat = P.grad.clone()
+    allreduce_gradients(flat, world)
+    if rank == 0:
+        Ps = P0.clone().requires_grad_(True)
+        full = sum(_view_grad(sc, b, Ps, n_grid, meta, env, 1.0 / V, total_pn, 0.3) for b in view_ids)
+        full.backward()
+        err = float((flat - Ps.grad).norm() / Ps.grad.norm())
+        ret["err"] = err
+        ret["nnz"] = int((flat != 0).sum())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gradient_equals_single_process():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["nnz"] > 100
+    assert ret["err"] < 1e-5, ret["err"]
+
+
+def test_shard_slice_validation():
+    from dreammat_b200.parallel import shard_slice
+    assert shard_slice(8, 3, 4) == slice(6, 8)
+    try:
+        shard_slice(8, 0, 3)
+        assert False
+    except ValueError:
+        pass
