@@ -38,63 +38,111 @@ __device__ __forceinline__ float silu_grad(float x) {
 
 // ----------------------------------------------------------------------------------- GroupNorm
 // stats[(img*G + g)*2 + {0,1}] += (sum, sumsq) over the group's channels and the pixel chunk.
-// One thread owns one channel PAIR (cpg is even for every SD layer) and strides over pixels.
+// One thread owns one 8-channel vector (16 B) and strides over pixels with 4 independent loads in flight;
+// channel PAIRS never straddle a group (cpg is even for every SD layer), so each thread keeps 4 (sum, sumsq)
+// pairs and folds them into the block's shared accumulators once.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int G,
                                                        int chunks, float* __restrict__ stats) {
     extern __shared__ float s_acc[];  // [G*2]
     const int img = blockIdx.y, chunk = blockIdx.x;
-    const int pairs = C / 2, cpg = C / G;
+    const int vpp = C / 8, cpg = C / G;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
     const int px_per_chunk = (HW + chunks - 1) / chunks;
     const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / pairs);   // pixel lanes when pairs < blockDim
-    for (int pr = threadIdx.x % max(pairs, 1); pr < pairs; pr += blockDim.x) {
-        int q = (pairs < (int)blockDim.x) ? threadIdx.x / pairs : 0;
-        if (pairs < (int)blockDim.x && q >= lanes) break;
-        float s = 0.f, ss = 0.f;
-        const T* base = x + ((int64_t)img * HW) * ld + 2 * pr;
-        for (int p = p0 + q; p < p1; p += lanes) {
-            const T* px = base + (int64_t)p * ld;
-            float a = H<T>::f(px[0]), b = H<T>::f(px[1]);
-            s += a + b; ss += a * a + b * b;
+    const int lanes = max(1, (int)blockDim.x / vpp);
+    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
+    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
+        float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+        const T* base = x + ((int64_t)img * HW) * ld + 8 * v;
+        int p = p0 + q;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (int64_t)(p + k * lanes) * ld);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const T* h = reinterpret_cast<const T*>(&u[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = H<T>::f(h[2 * j]), b = H<T>::f(h[2 * j + 1]);
+                    s[j] += a + b; ss[j] += a * a + b * b;
+                }
+            }
         }
-        int g = (2 * pr) / cpg;
-        atomicAdd(&s_acc[2 * g], s); atomicAdd(&s_acc[2 * g + 1], ss);
-        if (pairs >= (int)blockDim.x) continue; else break;
+        for (; p < p1; p += lanes) {
+            uint4 u = *reinterpret_cast<const uint4*>(base + (int64_t)p * ld);
+            const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a = H<T>::f(h[2 * j]), b = H<T>::f(h[2 * j + 1]);
+                s[j] += a + b; ss[j] += a * a + b * b;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * v + 2 * j) / cpg;
+            atomicAdd(&s_acc[2 * g], s[j]); atomicAdd(&s_acc[2 * g + 1], ss[j]);
+        }
+        if (vpp <= (int)blockDim.x) break;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + ((int64_t)img * G) * 2 + i, s_acc[i]);
 }
 
-// y = act((x - mean) * rstd * gamma + beta), 8 channels (16 B) per thread
+// y = act(x * A[c] + B[c]) with A = rstd*gamma, B = beta - mean*rstd*gamma.  Same thread mapping as the stats
+// kernel (one fixed 8-channel vector per thread, striding over pixels), so A/B live in 16 registers and the
+// loop body is load-16B / 8 FMA (+SiLU) / store-16B with 4 independent loads in flight.
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int64_t n_vec, int HW, int C, int ld,
-                                                       int ldy, int G, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int HW, int C, int ld, int ldy, int G,
+                                                       int chunks, const float* __restrict__ stats,
                                                        const T* __restrict__ gamma, const T* __restrict__ beta,
                                                        float eps, int silu, T* __restrict__ y) {
-    const int vec_per_px = C / 8, cpg = C / G;
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int vpp = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t px = i / vec_per_px; int c0 = (int)(i - px * vec_per_px) * 8;
-        int img = (int)(px / HW);
-        uint4 u = *reinterpret_cast<const uint4*>(x + px * ld + c0);
-        const T* h = reinterpret_cast<const T*>(&u);
-        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+    const int px_per_chunk = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
+    const int lanes = max(1, (int)blockDim.x / vpp);
+    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
+    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
+        float A[8], Bc[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            int g = (c0 + j) / cpg;
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * v + 2 * j) / cpg;
             float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
-            float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+            float mean = s * inv_cnt, rstd = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                float v = (H<T>::f(h[j + k]) - mean) * rstd * H<T>::f(gamma[c0 + j + k]) + H<T>::f(beta[c0 + j + k]);
-                if (silu) v = silu_f(v);
-                oh[j + k] = H<T>::t(v);
+                float gm = H<T>::f(gamma[8 * v + 2 * j + k]);
+                A[2 * j + k] = rstd * gm;
+                Bc[2 * j + k] = H<T>::f(beta[8 * v + 2 * j + k]) - mean * rstd * gm;
             }
         }
-        *reinterpret_cast<uint4*>(y + px * ldy + c0) = o;
+        const T* xb = x + ((int64_t)img * HW) * ld + 8 * v;
+        T* yb = y + ((int64_t)img * HW) * ldy + 8 * v;
+        auto body = [&](uint4 u, int p) {
+            const T* h = reinterpret_cast<const T*>(&u);
+            uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float val = fmaf(H<T>::f(h[k]), A[k], Bc[k]);
+                if (silu) val = silu_f(val);
+                oh[k] = H<T>::t(val);
+            }
+            *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = o;
+        };
+        int p = p0 + q;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + k * lanes) * ld);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) body(u[k], p + k * lanes);
+        }
+        for (; p < p1; p += lanes) body(*reinterpret_cast<const uint4*>(xb + (int64_t)p * ld), p);
+        if (vpp <= (int)blockDim.x) break;
     }
 }
 
@@ -105,77 +153,100 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
                                                            const T* __restrict__ gamma, const T* __restrict__ beta,
                                                            float eps, int silu, float* __restrict__ bstats) {
     extern __shared__ float s_acc[];
-    const int img = blockIdx.y, chunk = blockIdx.x, cpg = C / G, pairs = C / 2;
+    const int img = blockIdx.y, chunk = blockIdx.x, cpg = C / G, vpp = C / 8;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
     const int px_per_chunk = (HW + chunks - 1) / chunks;
     const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / pairs);
-    for (int pr = threadIdx.x % pairs; pr < pairs; pr += blockDim.x) {
-        int q = (pairs < (int)blockDim.x) ? threadIdx.x / pairs : 0;
-        if (pairs < (int)blockDim.x && q >= lanes) break;
-        int g = (2 * pr) / cpg;
-        float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
-        float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
-        float g0 = H<T>::f(gamma[2 * pr]), g1 = H<T>::f(gamma[2 * pr + 1]);
-        float b0 = H<T>::f(beta[2 * pr]), b1 = H<T>::f(beta[2 * pr + 1]);
-        float a1 = 0.f, a2 = 0.f;
-        for (int p = p0 + q; p < p1; p += lanes) {
-            int64_t off = ((int64_t)img * HW + p) * C + 2 * pr;
-            float xh0 = (H<T>::f(x[off]) - mean) * rstd, xh1 = (H<T>::f(x[off + 1]) - mean) * rstd;
-            float d0 = H<T>::f(dz[off]), d1 = H<T>::f(dz[off + 1]);
-            if (silu) { d0 *= silu_grad(xh0 * g0 + b0); d1 *= silu_grad(xh1 * g1 + b1); }
-            a1 += g0 * d0 + g1 * d1;
-            a2 += g0 * d0 * xh0 + g1 * d1 * xh1;
+    const int lanes = max(1, (int)blockDim.x / vpp);
+    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
+    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
+        float mean[4], rstd[4], gm[8], bt[8], a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * v + 2 * j) / cpg;
+            float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
+            mean[j] = s * inv_cnt;
+            rstd[j] = rsqrtf(fmaxf(ss * inv_cnt - mean[j] * mean[j], 0.f) + eps);
         }
-        atomicAdd(&s_acc[2 * g], a1); atomicAdd(&s_acc[2 * g + 1], a2);
-        if (pairs >= (int)blockDim.x) continue; else break;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gm[k] = H<T>::f(gamma[8 * v + k]); bt[k] = H<T>::f(beta[8 * v + k]); }
+        const int64_t base = ((int64_t)img * HW) * C + 8 * v;
+        for (int p = p0 + q; p < p1; p += lanes) {
+            uint4 ux = *reinterpret_cast<const uint4*>(x + base + (int64_t)p * C);
+            uint4 ud = *reinterpret_cast<const uint4*>(dz + base + (int64_t)p * C);
+            const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float xh = (H<T>::f(hx[k]) - mean[k >> 1]) * rstd[k >> 1];
+                float d = H<T>::f(hd[k]);
+                if (silu) d *= silu_grad(xh * gm[k] + bt[k]);
+                a1[k >> 1] += gm[k] * d;
+                a2[k >> 1] += gm[k] * d * xh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * v + 2 * j) / cpg;
+            atomicAdd(&s_acc[2 * g], a1[j]); atomicAdd(&s_acc[2 * g + 1], a2[j]);
+        }
+        if (vpp <= (int)blockDim.x) break;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(bstats + ((int64_t)img * G) * 2 + i, s_acc[i]);
 }
 
-// backward pass 2: dx = rstd * (gamma*dy' - (S1 + xhat*S2)/cnt)  (+ dx_add if given)
+// backward pass 2: dx = rstd * (gamma*dy' - (S1 + xhat*S2)/cnt)  (+ dx_add if given); same mapping as gn_apply
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dz,
-                                                           int64_t n_vec, int HW, int C, int G,
-                                                           const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dz, int HW,
+                                                           int C, int G, int chunks, const float* __restrict__ stats,
                                                            const float* __restrict__ bstats,
                                                            const T* __restrict__ gamma, const T* __restrict__ beta,
                                                            float eps, int silu, const T* __restrict__ dx_add,
                                                            T* __restrict__ dx) {
-    const int vec_per_px = C / 8, cpg = C / G;
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int vpp = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t px = i / vec_per_px; int c0 = (int)(i - px * vec_per_px) * 8;
-        int img = (int)(px / HW);
-        uint4 ux = *reinterpret_cast<const uint4*>(x + px * C + c0);
-        uint4 ud = *reinterpret_cast<const uint4*>(dz + px * C + c0);
-        uint4 ua = make_uint4(0, 0, 0, 0);
-        if (dx_add) ua = *reinterpret_cast<const uint4*>(dx_add + px * C + c0);
-        const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
-        const T* ha = reinterpret_cast<const T*>(&ua);
-        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+    const int px_per_chunk = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
+    const int lanes = max(1, (int)blockDim.x / vpp);
+    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
+    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
+        float mean[4], rstd[4], S1[4], S2[4], gm[8], bt[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            int g = (c0 + j) / cpg;
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * v + 2 * j) / cpg;
             int64_t si = ((int64_t)img * G + g) * 2;
             float s = stats[si], ss = stats[si + 1];
-            float mean = s * inv_cnt, var = fmaxf(ss * inv_cnt - mean * mean, 0.f), rstd = rsqrtf(var + eps);
-            float S1 = bstats[si] * inv_cnt, S2 = bstats[si + 1] * inv_cnt;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float gm = H<T>::f(gamma[c0 + j + k]), bt = H<T>::f(beta[c0 + j + k]);
-                float xh = (H<T>::f(hx[j + k]) - mean) * rstd;
-                float d = H<T>::f(hd[j + k]);
-                if (silu) d *= silu_grad(xh * gm + bt);
-                float v = rstd * (gm * d - S1 - xh * S2);
-                if (dx_add) v += H<T>::f(ha[j + k]);
-                oh[j + k] = H<T>::t(v);
-            }
+            mean[j] = s * inv_cnt;
+            rstd[j] = rsqrtf(fmaxf(ss * inv_cnt - mean[j] * mean[j], 0.f) + eps);
+            S1[j] = bstats[si] * inv_cnt; S2[j] = bstats[si + 1] * inv_cnt;
         }
-        *reinterpret_cast<uint4*>(dx + px * C + c0) = o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gm[k] = H<T>::f(gamma[8 * v + k]); bt[k] = H<T>::f(beta[8 * v + k]); }
+        const int64_t base = ((int64_t)img * HW) * C + 8 * v;
+        for (int p = p0 + q; p < p1; p += lanes) {
+            const int64_t off = base + (int64_t)p * C;
+            uint4 ux = *reinterpret_cast<const uint4*>(x + off);
+            uint4 ud = *reinterpret_cast<const uint4*>(dz + off);
+            uint4 ua = make_uint4(0, 0, 0, 0);
+            if (dx_add) ua = *reinterpret_cast<const uint4*>(dx_add + off);
+            const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
+            const T* ha = reinterpret_cast<const T*>(&ua);
+            uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float xh = (H<T>::f(hx[k]) - mean[k >> 1]) * rstd[k >> 1];
+                float d = H<T>::f(hd[k]);
+                if (silu) d *= silu_grad(xh * gm[k] + bt[k]);
+                float val = rstd[k >> 1] * (gm[k] * d - S1[k >> 1] - xh * S2[k >> 1]);
+                if (dx_add) val += H<T>::f(ha[k]);
+                oh[k] = H<T>::t(val);
+            }
+            *reinterpret_cast<uint4*>(dx + off) = o;
+        }
+        if (vpp <= (int)blockDim.x) break;
     }
 }
 
@@ -430,7 +501,7 @@ inline int grid_for(int64_t work, int threads = 256) {
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 inline int gn_chunks(int n_img, int HW) {
-    int c = (DM_NUM_SMS * 4) / (n_img > 0 ? n_img : 1);
+    int c = (DM_NUM_SMS * 8) / (n_img > 0 ? n_img : 1);
     if (c < 1) c = 1;
     int maxc = HW / 64; if (maxc < 1) maxc = 1;
     return c < maxc ? c : maxc;
@@ -448,9 +519,8 @@ extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, i
     int threads = 256;
     DM_DISPATCH_T(bf16, gn_stats_kernel<T><<<dim3(chunks, n_img), threads, 2 * G * sizeof(float), st>>>((const T*)x, HW, C, ld, G, chunks, stats));
     DM_CHECK_LAUNCH();
-    int64_t n_vec = (int64_t)n_img * HW * (C / 8);
-    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<grid_for(n_vec), 256, 0, st>>>((const T*)x, n_vec, HW, C, ld, ldy, G, stats, (const T*)gamma,
-                                                                         (const T*)beta, eps, silu, (T*)y));
+    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<dim3(chunks, n_img), 256, 0, st>>>((const T*)x, HW, C, ld, ldy, G, chunks, stats, (const T*)gamma,
+                                                                             (const T*)beta, eps, silu, (T*)y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -466,10 +536,9 @@ extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_i
     DM_DISPATCH_T(bf16, gn_bwd_stats_kernel<T><<<dim3(chunks, n_img), 256, 2 * G * sizeof(float), st>>>(
                             (const T*)x, (const T*)dz, HW, C, G, chunks, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats));
     DM_CHECK_LAUNCH();
-    int64_t n_vec = (int64_t)n_img * HW * (C / 8);
-    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<grid_for(n_vec), 256, 0, st>>>((const T*)x, (const T*)dz, n_vec, HW, C, G, stats, bstats,
-                                                                             (const T*)gamma, (const T*)beta, eps, silu,
-                                                                             (const T*)dx_add, (T*)dx));
+    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<dim3(chunks, n_img), 256, 0, st>>>((const T*)x, (const T*)dz, HW, C, G, chunks, stats, bstats,
+                                                                                 (const T*)gamma, (const T*)beta, eps, silu,
+                                                                                 (const T*)dx_add, (T*)dx));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

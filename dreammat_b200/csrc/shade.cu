@@ -107,11 +107,20 @@ struct McParams {
     float *color, *jac, *reg_sums;
     float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
     uint32_t* hit_bits;
+    const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
-__global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
+// Per-pixel quantities are warp-uniform; they live in shared memory (one record per warp) instead of being
+// replicated in 32 lanes' registers -- the traversal loop is latency-bound and wants occupancy.
+struct PixState {
+    float p[3], n[3], v[3], r[3], xd[3], yd[3], xs[3], ys[3];
+    float a, NoV, rd, rs, g1v, g1d;
+};
+
+__global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
+    __shared__ PixState s_px[MC_WARPS];
     __shared__ float s_reg[2];
     const int nd = P.cfg.n_diffuse, ns = P.cfg.n_specular, S = nd + ns;
     float* s_td = s_tab;
@@ -130,7 +139,6 @@ __global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t pix = (int64_t)blockIdx.x * MC_WARPS + warp;
-    float reg_kd = 0.f, reg_ks = 0.f;
     if (pix < P.n) {
         // coalesced staging of the 19 per-pixel input floats through shared memory
         if (lane < 3) s_in[warp][lane] = P.pts[3 * pix + lane];
@@ -140,88 +148,94 @@ __global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
         else if (lane < 19) s_in[warp][lane] = P.features_jitter[5 * pix + lane - 14];
         __syncwarp();
         const float* si = s_in[warp];
-        const f3 p = mk3(si[0], si[1], si[2]), n = mk3(si[3], si[4], si[5]), v = mk3(si[6], si[7], si[8]);
-        float m[5], mj[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(si[9 + k]); mj[k] = sigmoidf_(si[14 + k]); }
-        // material_smoothness_grad (:110-123)
-        {
-            float k0 = fabsf(m[0] - mj[0]), k1 = fabsf(m[1] - mj[1]), k2 = fabsf(m[2] - mj[2]);
-            reg_kd = ((k0 + k1 + k2) / 3.0f) * k2;
-            reg_ks = fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
+        PixState& px = s_px[warp];
+        if (lane == 0) {
+            const f3 p = mk3(si[0], si[1], si[2]), n = mk3(si[3], si[4], si[5]), v = mk3(si[6], si[7], si[8]);
+            const float a = sigmoidf_(si[13]) * (P.cfg.max_roughness - P.cfg.min_roughness) + P.cfg.min_roughness;
+            const float ndv = dot3(v, n);
+            const f3 r = (ndv * n) * 2.0f - v;  // reflections (:620)
+            const f3 xd = ortho_dir(n), yd = cross3(n, xd), xs = ortho_dir(r), ys = cross3(r, xs);
+            const float NoV = fminf(fmaxf(ndv, 0.f), 1.f);
+            const Dual g1 = ggx_G1(mkd(NoV), mkd(a, 1.0f));
+            px.p[0] = p.x; px.p[1] = p.y; px.p[2] = p.z; px.n[0] = n.x; px.n[1] = n.y; px.n[2] = n.z;
+            px.v[0] = v.x; px.v[1] = v.y; px.v[2] = v.z; px.r[0] = r.x; px.r[1] = r.y; px.r[2] = r.z;
+            px.xd[0] = xd.x; px.xd[1] = xd.y; px.xd[2] = xd.z; px.yd[0] = yd.x; px.yd[1] = yd.y; px.yd[2] = yd.z;
+            px.xs[0] = xs.x; px.xs[1] = xs.y; px.xs[2] = xs.z; px.ys[0] = ys.x; px.ys[1] = ys.y; px.ys[2] = ys.z;
+            px.a = a; px.NoV = NoV; px.g1v = g1.v; px.g1d = g1.d;
+            px.rd = P.rand_d[pix] * PI_F * 2.0f; px.rs = P.rand_s[pix] * PI_F * 2.0f;
         }
-        const float alb[3] = {fminf(fmaxf(m[0], 0.f), 1.f), fminf(fmaxf(m[1], 0.f), 1.f), fminf(fmaxf(m[2], 0.f), 1.f)};
-        const float met = m[3] * (P.cfg.max_metallic - P.cfg.min_metallic) + P.cfg.min_metallic;
-        const float a = m[4] * (P.cfg.max_roughness - P.cfg.min_roughness) + P.cfg.min_roughness;
-        const float ndv = dot3(v, n);
-        const f3 r = (ndv * n) * 2.0f - v;  // reflections (:620)
-        const float NoV = fminf(fmaxf(ndv, 0.f), 1.f);
-        const f3 xd = ortho_dir(n), yd = cross3(n, xd);
-        const f3 xs = ortho_dir(r), ys = cross3(r, xs);
-        const float rd_ = P.rand_d[pix] * PI_F * 2.0f, rs_ = P.rand_s[pix] * PI_F * 2.0f;
+        __syncwarp();
         const float kd_pdf = (float)nd / (float)(ns + nd), ks_pdf = (float)ns / (float)(ns + nd);
-        const Dual aD = mkd(a, 1.0f);
-        const Dual G1v = ggx_G1(mkd(NoV), aD);
 
         float Ld[3] = {0, 0, 0}, Ls[3] = {0, 0, 0};
         float U[3] = {0, 0, 0}, V[3] = {0, 0, 0};      // sum L*w, sum L*w*fh
         float Ud[3] = {0, 0, 0}, Vd[3] = {0, 0, 0};    // d/da of the above with fh held fixed
         float Wd[3] = {0, 0, 0};                       // sum L*w*dfh/da
-        uint32_t hitword = 0;
 
-        for (int s0 = 0; s0 < S; s0 += 32) {
-            const int s = s0 + lane;
+        const int it_d = (nd + 31) >> 5, it_s = (ns + 31) >> 5;
+        for (int it = 0; it < it_d + it_s; ++it) {
+            // the two sample families are visited in separate warp-aligned segments so a warp never mixes them
+            const bool spec = it >= it_d;
+            const int slot = (spec ? (it - it_d) : it) * 32 + lane;
+            const bool active = slot < (spec ? ns : nd);
+            int s = spec ? nd + slot : slot;
+            if (active && P.perm) s = P.perm[s];
             bool hit = true;
-            if (s < S) {
+            if (active) {
+                // ---- sample direction (value and d/da), :554-596
                 D3 d;
-                const bool spec = s >= nd;
                 if (!spec) {
-                    float az = s_td[3 * s] + rd_;
+                    float az = s_td[3 * s] + px.rd;
                     az = az - floorf(az / TWO_PI_F) * TWO_PI_F;  // % (2 pi)
                     float sn, cs;
                     sincosf(az, &sn, &cs);
                     float cx = s_td[3 * s + 1] * cs, cy = s_td[3 * s + 1] * sn, cz = s_td[3 * s + 2];
-                    f3 dv = cx * xd + cy * yd + cz * n;
-                    d.x = mkd(dv.x); d.y = mkd(dv.y); d.z = mkd(dv.z);
+                    d.x = mkd(cx * px.xd[0] + cy * px.yd[0] + cz * px.n[0]);
+                    d.y = mkd(cx * px.xd[1] + cy * px.yd[1] + cz * px.n[1]);
+                    d.z = mkd(cx * px.xd[2] + cy * px.yd[2] + cz * px.n[2]);
                 } else {
                     const int j = s - nd;
                     float ue = s_ts[2 * j + 1];
-                    float phi = s_ts[2 * j] + rs_;
+                    float phi = s_ts[2 * j] + px.rs;
                     phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
                     float sn, cs;
                     sincosf(phi, &sn, &cs);
+                    const Dual aD = mkd(px.a, 1.0f);
                     // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
                     Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
                     Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
                     Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
                     Dual cx = st * cs, cy = st * sn;
-                    d.x = cx * xs.x + cy * ys.x + ct * r.x;
-                    d.y = cx * xs.y + cy * ys.y + ct * r.y;
-                    d.z = cx * xs.z + cy * ys.z + ct * r.z;
+                    d.x = cx * px.xs[0] + cy * px.ys[0] + ct * px.r[0];
+                    d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
+                    d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
                 }
                 const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
-                // half vector H = normalize(v + d) (:513-514)
-                D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;
-                Dual hl2 = ddot(h, h);
-                Dual hl = dsqrt(hl2);
-                float hlc = fmaxf(hl.v, 1e-12f);
-                Dual hinv = mkd(1.0f / hlc, (hl.v > 1e-12f) ? (-hl.d / (hlc * hlc)) : 0.0f);
-                D3 Hh; Hh.x = h.x * hinv; Hh.y = h.y * hinv; Hh.z = h.z * hinv;
-                Dual HoV = dclamp01(ddot(Hh, v));
-                Dual fh = dpow5(dclamp01(1.0f - HoV));
-                Dual NoL = dclamp01(ddot(d, n));
-                Dual NoH = dclamp01(ddot(Hh, n));
-                Dual Dg = ggx_D(NoH, aD);
-                Dual G = G1v * ggx_G1(NoL, aD);
-                Dual pdf;
-                if (!spec) pdf = mkd(NoL.v / PI_F * kd_pdf);
-                else pdf = Dg * NoH / (4.0f * HoV + 1e-5f) * ks_pdf;
-                Dual w = Dg * G / (4.0f * NoV * pdf + 1e-5f);
-                // occlusion + light (:490-507)
-                f3 o = p + dv * 1e-5f;
-                float bt, bu, bvv; int bid;
-                hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+                // ---- occlusion first (:490-507): occluded samples contribute nothing, skip their BRDF math
+                {
+                    f3 o = mk3(px.p[0], px.p[1], px.p[2]) + dv * 1e-5f;
+                    float bt, bu, bvv; int bid;
+                    hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+                }
                 if (!hit) {
+                    const f3 n = mk3(px.n[0], px.n[1], px.n[2]), v = mk3(px.v[0], px.v[1], px.v[2]);
+                    const Dual aD = mkd(px.a, 1.0f);
+                    // half vector H = normalize(v + d) (:513-514)
+                    D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;
+                    Dual hl = dsqrt(ddot(h, h));
+                    float hlc = fmaxf(hl.v, 1e-12f);
+                    Dual hinv = mkd(1.0f / hlc, (hl.v > 1e-12f) ? (-hl.d / (hlc * hlc)) : 0.0f);
+                    D3 Hh; Hh.x = h.x * hinv; Hh.y = h.y * hinv; Hh.z = h.z * hinv;
+                    Dual HoV = dclamp01(ddot(Hh, v));
+                    Dual fh = dpow5(dclamp01(1.0f - HoV));
+                    Dual NoL = dclamp01(ddot(d, n));
+                    Dual NoH = dclamp01(ddot(Hh, n));
+                    Dual Dg = ggx_D(NoH, aD);
+                    Dual G = mkd(px.g1v, px.g1d) * ggx_G1(NoL, aD);
+                    Dual pdf;
+                    if (!spec) pdf = mkd(NoL.v / PI_F * kd_pdf);
+                    else pdf = Dg * NoH / (4.0f * HoV + 1e-5f) * ks_pdf;
+                    Dual w = Dg * G / (4.0f * px.NoV * pdf + 1e-5f);
                     float4 L4 = env_fetch(P.env, P.envH, P.envW, dv);
                     const float L[3] = {L4.x, L4.y, L4.z};
 #pragma unroll
@@ -235,12 +249,8 @@ __global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
                     }
                 }
             }
-            if (P.hit_bits) {
-                uint32_t b = __ballot_sync(0xffffffffu, hit && (s < S));
-                if (lane == (s0 >> 5)) hitword = b;
-            }
+            if (P.hit_bits && active && hit) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
         }
-        if (P.hit_bits && lane < (S + 31) / 32) P.hit_bits[pix * ((S + 31) / 32) + lane] = hitword;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             Ld[c] = warp_sum(Ld[c]); Ls[c] = warp_sum(Ls[c]);
@@ -248,6 +258,16 @@ __global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
             Ud[c] = warp_sum(Ud[c]); Vd[c] = warp_sum(Vd[c]); Wd[c] = warp_sum(Wd[c]);
         }
         if (lane == 0) {
+            float m[5], mj[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(si[9 + k]); mj[k] = sigmoidf_(si[14 + k]); }
+            // material_smoothness_grad (:110-123)
+            float k0 = fabsf(m[0] - mj[0]), k1 = fabsf(m[1] - mj[1]), k2 = fabsf(m[2] - mj[2]);
+            const float reg_kd = ((k0 + k1 + k2) / 3.0f) * k2;
+            const float reg_ks = fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
+            const float alb[3] = {fminf(fmaxf(m[0], 0.f), 1.f), fminf(fmaxf(m[1], 0.f), 1.f), fminf(fmaxf(m[2], 0.f), 1.f)};
+            const float met = m[3] * (P.cfg.max_metallic - P.cfg.min_metallic) + P.cfg.min_metallic;
+            const float a = px.a;
             const float invS = 1.0f / (float)S, invd = 1.0f / (float)nd, invs = 1.0f / (float)ns;
             float colv[3], specv[3], diffv[3];
 #pragma unroll
@@ -279,6 +299,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) shade_mc_kernel(McParams P) {
     __syncthreads();
     if (threadIdx.x < 2 && P.reg_sums) atomicAdd(P.reg_sums + threadIdx.x, s_reg[threadIdx.x]);
 }
+
 
 // ------------------------------------------------------------------------------------------ split-sum
 
@@ -482,7 +503,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
                                const float* rand_d, const float* rand_s, int64_t n, float* color, float* jac,
                                float* reg_sums, float* albedo, float* roughness, float* metalness, float* spec_light,
                                float* diff_light, float* spec_color, float* diff_color, uint32_t* hit_bits,
-                               void* stream) {
+                               const int32_t* sample_perm, void* stream) {
     if (n == 0) return DM_OK;
     DM_REQUIRE(cfg && bvh && env_rgba && tab_d && tab_s && pts && normals && viewdirs && features && features_jitter &&
                    rand_d && rand_s && color && jac, "null pointer");
@@ -493,7 +514,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.pts = pts; P.normals = normals; P.viewdirs = viewdirs; P.features = features; P.features_jitter = features_jitter;
     P.rand_d = rand_d; P.rand_s = rand_s; P.n = n; P.color = color; P.jac = jac; P.reg_sums = reg_sums;
     P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
-    P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits;
+    P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
     size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float);
     shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();

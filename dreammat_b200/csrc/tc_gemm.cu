@@ -303,9 +303,12 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p
     return DM_EUNSUPPORTED;
 }
 
-int pick_bn(int N, int bn_hint) {
+int pick_bn(int64_t M, int N, int bn_hint) {
     if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
     if (N <= 64) return 64;
+    // too few 128x128 tiles to fill 148 SMs x 2 resident CTAs: halve the tile width (low-resolution UNet levels)
+    int64_t tiles128 = dm_ceil_div(M, BM) * dm_ceil_div(N, 128);
+    if (tiles128 < (int64_t)DM_NUM_SMS * 3 / 2) return 64;
     if (N % 128 == 0) return 128;
     if (N % 64 == 0 && N < 512) return 64;
     return 128;
@@ -335,7 +338,7 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
     DM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "row strides must be multiples of 8 elements (16 bytes)");
     DM_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "16-byte aligned operands");
     if (batch < 1) batch = 1;
-    int bn = pick_bn(N, bn_hint);
+    int bn = pick_bn((int64_t)M * (batch > 1 ? batch : 1), N, bn_hint);
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
@@ -375,7 +378,7 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     int tile_n = BM / (tile_w * tile_h);
     DM_REQUIRE(tile_w * tile_h * tile_n == BM && Wo % tile_w == 0 && Ho % tile_h == 0,
                "output extent must tile into 128-pixel boxes (power-of-two sizes)");
-    int bn = pick_bn(Cout, bn_hint);
+    int bn = pick_bn((int64_t)n_img * Ho * Wo, Cout, bn_hint);
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};

@@ -115,6 +115,77 @@ class _SDSLoss(torch.autograd.Function):
         return dlat * g, None, None
 
 
+class _DenseGraphs:
+    """Static buffers + three captured CUDA graphs for the dense section (shapes fixed by B, H, W)."""
+
+    def __init__(self, guid, B, H, W):
+        self.guid, self.B = guid, B
+        dev, dt = guid.device, guid.weights_dtype
+        h, w = H // 8, W // 8
+        Dm = guid.unet.cfg.cross_attention_dim
+        self.rgb = torch.ones(B, H, W, 3, device=dev)
+        self.vae_eps = torch.zeros(B, 4, h, w, device=dev)
+        self.noise = torch.zeros(B, 4, h, w, device=dev)
+        self.sqrt_ac, self.sqrt_1mac = torch.ones(B, device=dev), torch.zeros(B, device=dev)
+        self.t3 = torch.full((3 * B,), 500.0, device=dev)
+        self.ctx = torch.zeros(3 * B, 77, Dm, device=dev, dtype=dt)
+        self.cond = torch.zeros(B, H, W, 22, device=dev)
+        self.dz = torch.zeros(B, 4, h, w, device=dev)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.cond_scale = None
+        # eager warm-up on a side stream (first-launch attribute setup must not happen under capture)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._vae_fwd(); self._unet(1.0); self._vae_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from ._cabi import lib
+        self.replayed_launches = 0          # kernels launched through graph replays (for bench.py's gpu_launches)
+        n0 = lib().dm_launch_count()
+        self.g_vae = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_vae, pool=self.pool):
+            self._vae_fwd()
+        self.n_vae = lib().dm_launch_count() - n0
+        self.capture_unet(float(guid.cfg.condition_scales[0]) if guid.use_controlnet else 0.0)
+        n0 = lib().dm_launch_count()
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=self.pool):
+            self._vae_bwd()
+        self.n_bwd = lib().dm_launch_count() - n0
+
+    def _vae_fwd(self):
+        g = self.guid
+        x = D.pad_convert(self.rgb, 64, 2.0, -1.0, g.weights_dtype)
+        self.tape = []
+        self.mom = g.vae.encode_moments(x, self.tape)
+        self.z = D.vae_sample(self.mom, self.vae_eps, g.vae.cfg.scaling_factor)
+
+    def _unet(self, scale):
+        g = self.guid
+        zt = D.add_noise(self.z, self.noise, self.sqrt_ac, self.sqrt_1mac, rep=3, cpad=64, dtype=g.weights_dtype)
+        down = mid = None
+        if g.use_controlnet and scale != 0:
+            cond = D.pad_convert(self.cond, 64, 1.0, 0.0, g.weights_dtype)
+            down, mid = g.controlnet.forward(zt, self.t3, self.ctx, cond, scale)
+        self.eps = g.unet.forward(zt, self.t3, self.ctx, down, mid)
+
+    def _vae_bwd(self):
+        g = self.guid
+        dmom = D.vae_sample_bwd(self.mom, self.vae_eps, self.dz, g.vae.cfg.scaling_factor)
+        dx = g.vae.backward_input(list(self.tape), dmom)
+        self.drgb = D.unpad_convert(dx, 3, 2.0)
+
+    def capture_unet(self, scale):
+        from ._cabi import lib
+        self.cond_scale = scale
+        n0 = lib().dm_launch_count()
+        self.g_unet = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_unet, pool=self.pool):
+            self._unet(scale)
+        self.n_unet = lib().dm_launch_count() - n0
+
+
 class StableDiffusionLightGuidance:
     @dataclass
     class Config:
@@ -166,6 +237,7 @@ class StableDiffusionLightGuidance:
         self.alphas = alphas_cumprod().to(self.device)
         self.set_min_max_steps()
         self.update_step(0, 0)
+        self.graphs = None
 
     # ---- schedules (dreammat_guidance.py:604-626)
     def set_min_max_steps(self, min_step_percent=0.02, max_step_percent=0.98):
@@ -219,6 +291,51 @@ class StableDiffusionLightGuidance:
         w = (1 - self.alphas[t]).float()
         return R.sds_grad(eps, noise, w, float(self.cond_scale), float(self.uncond_scale), float(self.null_scale),
                           float(self.noise_scale))
+
+    # ---- CUDA-graph path: the dense section has static shapes, so its ~900 launches are captured once
+    def enable_graphs(self, B: int, H: int, W: int):
+        """Capture (1) VAE encode, (2) add_noise + ControlNet + UNet, (3) the VAE input-gradient as three CUDA graphs
+        over static buffers.  Schedules that change kernel arguments (the ControlNet scale) trigger a re-capture."""
+        self.graphs = _DenseGraphs(self, B, H, W)
+        return self.graphs
+
+    def graph_step(self, cond_bhwc, ctx3, grad_scale: float, t=None, noise=None, vae_eps=None, mark=None):
+        """One guidance evaluation through the captured graphs.  `graphs.rgb` must hold the rendered batch.
+        Returns (d loss / d rgb [B,H,W,3], sums[10]) with d loss_sds / d latents = grad / B * grad_scale."""
+        g = self.graphs
+        B = g.B
+        scale = float(self.cfg.condition_scales[0]) if self.use_controlnet else 0.0
+        if scale != g.cond_scale:
+            g.capture_unet(scale)
+        if vae_eps is None:
+            g.vae_eps.normal_()
+        else:
+            g.vae_eps.copy_(vae_eps)
+        g.g_vae.replay()
+        if mark:
+            mark("vae_fwd")
+        if t is None:
+            t = torch.randint(self.min_step, self.max_step + 1, [B], dtype=torch.long, device=self.device)
+        if noise is None:
+            g.noise.normal_()
+        else:
+            g.noise.copy_(noise)
+        ac = self.alphas[t]
+        g.sqrt_ac.copy_(ac.sqrt()); g.sqrt_1mac.copy_((1 - ac).sqrt()); g.t3.copy_(torch.cat([t] * 3).float())
+        g.ctx.copy_(ctx3)
+        g.cond.copy_(cond_bhwc)
+        g.g_unet.replay()
+        if mark:
+            mark("unet_cn")
+        grad, dlat, sums = R.sds_grad(g.eps.view(3, B, *g.eps.shape[1:]), g.noise, (1 - ac).float(), float(self.cond_scale),
+                                      float(self.uncond_scale), float(self.null_scale), float(self.noise_scale))
+        g.dz.copy_(dlat)
+        g.dz.mul_(grad_scale)
+        g.g_bwd.replay()
+        g.replayed_launches += g.n_vae + g.n_unet + g.n_bwd
+        if mark:
+            mark("vae_bwd")
+        return g.drgb, sums
 
     def __call__(self, rgb, prompt_utils: PromptProcessorOutput, elevation, azimuth, camera_distances, env_id=None,
                  rgb_as_latents=False, **kwargs) -> Dict[str, torch.Tensor]:

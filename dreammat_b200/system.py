@@ -141,6 +141,7 @@ class DreamMatMaterial:
         self.light = [R.envmap_pack(m.to(self.device)) for m in (env_maps or [])]
         self.tab_d = R.direction_tables(c.diffuse_sample_num).to(self.device)
         self.tab_s = R.direction_tables(c.specular_sample_num).to(self.device)
+        self.perm = R.sample_order(c.diffuse_sample_num, c.specular_sample_num).to(self.device)
         self.mc_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness_squre, c.max_roughness_squre,
                                   c.diffuse_sample_num, c.specular_sample_num)
         self.ss_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness, c.max_roughness,
@@ -164,7 +165,7 @@ class DreamMatMaterial:
             if rand_s is None:
                 rand_s = torch.rand(n, device=self.device)           # appendix B #6
             color, reg, aux = R.shade_mc(features, features_jitter, pts, normals, viewdirs, rand_d, rand_s, self.mc_cfg,
-                                         self.bvh, self.light[e], self.tab_d, self.tab_s, want_aux, reg_weight_n)
+                                         self.bvh, self.light[e], self.tab_d, self.tab_s, want_aux, reg_weight_n, self.perm)
         else:
             dcube, mips = self.envlight[e]
             color, reg, aux = R.shade_splitsum(features, features_jitter, normals, viewdirs, self.ss_cfg, self.FG_LUT,
@@ -291,7 +292,7 @@ class DreamMat:
         torch.cuda.synchronize()
         ev = self._events
         out = {ev[i][0] + "_ms": ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
-        out["dense_ms"] = out.get("vae_fwd_ms", 0) + out.get("unet_cn_ms", 0) + out.get("vae_bwd_ms", 0)
+        out["dense_ms"] = out.get("vae_fwd_ms", 0) + out.get("unet_cn_ms", 0) + out.get("vae_bwd_ms", 0) + out.get("dense_graphs_ms", 0)
         out["total_ms"] = ev[0][1].elapsed_time(ev[-1][1])
         return out
 
@@ -330,7 +331,8 @@ class DreamMat:
         gbs = [ren.gbuffer(batch["rays_o"][b:b + 1], batch["rays_d"][b:b + 1], batch["mvp_mtx"][b:b + 1],
                            batch["w2c"][b:b + 1], int(batch["view_id"][b])) for b in range(B)]
         total_pn = total_pn_global or sum(g["pn"] for g in gbs)
-        canvas = torch.empty(B, H * W, 3, device=dev)
+        g_ = getattr(guid, "graphs", None)
+        canvas = g_.rgb.view(B, H * W, 3) if (g_ is not None and g_.B == B and rng is None) else torch.empty(B, H * W, 3, device=dev)
         check(lib().dm_fill(ptr(canvas), canvas.numel(), 1.0, st), "dm_fill")
         reg_sums = torch.zeros(2, device=dev)
         saved = []
@@ -350,25 +352,33 @@ class DreamMat:
             check(lib().dm_shade_mc_fwd(C.byref(mat.mc_cfg), ren.ray_tracer.h, ptr(env), env.shape[0], env.shape[1],
                                         ptr(mat.tab_d), ptr(mat.tab_s), ptr(g["pts"]), ptr(g["nrm"]), ptr(g["vd"]), ptr(f),
                                         ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
-                                        None, st), "dm_shade_mc_fwd")
+                                        None, ptr(mat.perm), st), "dm_shade_mc_fwd")
             check(lib().dm_scatter_canvas(ptr(color), ptr(g["pix"]), n, 3, ptr(canvas[b]), st), "dm_scatter_canvas")
             saved.append((g, pj, f, fj, jac))
-        comp_rgb = canvas.view(B, H, W, 3).requires_grad_(True)
+        use_graphs = getattr(guid, "graphs", None) is not None and guid.graphs.B == B and rng is None
+        comp_rgb = canvas.view(B, H, W, 3)
         self._mark("render_fwd")
-        # guidance (dreammat_guidance.py:536-602): VAE encode with grad, ControlNet + UNet x3 under no_grad, CSD gradient
-        from .guidance import _SDSLoss
-        lat = guid.encode_images(comp_rgb, rng["vae_eps"].to(dev) if rng is not None else None)
-        self._mark("vae_fwd")
         ctx3 = self.prompt_utils.get_text_embeddings(batch["elevation"], batch["azimuth"], batch["camera_distances"],
                                                      guid.cfg.view_dependent_prompting, return_null_text_embeddings=True)
-        grad, dlat, sums = guid.compute_grad_sds(lat, batch["condition_map"], ctx3, rng["t"].to(dev) if rng is not None else None,
-                                                 rng["noise"].to(dev) if rng is not None else None)
-        self._mark("unet_cn")
-        loss_sds = _SDSLoss.apply(lat, dlat, sums[0] / B) * (B / Bg)          # mean over the GLOBAL batch of views
-        (lam_sds * loss_sds).backward()
-        self._mark("vae_bwd")
+        if use_graphs:
+            # dense section replayed from three captured CUDA graphs (VAE fwd | ControlNet+UNet | VAE bwd)
+            drgb, sums = guid.graph_step(batch["condition_map"], ctx3, lam_sds * B / Bg, mark=self._mark)
+            loss_sds = sums[0] / Bg
+            dcanvas = drgb.view(B, H * W, 3)
+        else:
+            # guidance (dreammat_guidance.py:536-602): VAE encode with grad, ControlNet + UNet x3 under no_grad, CSD gradient
+            from .guidance import _SDSLoss
+            comp_rgb.requires_grad_(True)
+            lat = guid.encode_images(comp_rgb, rng["vae_eps"].to(dev) if rng is not None else None)
+            self._mark("vae_fwd")
+            grad, dlat, sums = guid.compute_grad_sds(lat, batch["condition_map"], ctx3, rng["t"].to(dev) if rng is not None else None,
+                                                     rng["noise"].to(dev) if rng is not None else None)
+            self._mark("unet_cn")
+            loss_sds = _SDSLoss.apply(lat, dlat, sums[0] / B) * (B / Bg)          # mean over the GLOBAL batch of views
+            (lam_sds * loss_sds).backward()
+            self._mark("vae_bwd")
+            dcanvas = comp_rgb.grad.view(B, H * W, 3)
         gout = {"grad_norm": sums[1].sqrt()}
-        dcanvas = comp_rgb.grad.view(B, H * W, 3)
         # backward into the hash grid / MLP
         geo.grads.zero_()
         for b, (g, pj, f, fj, jac) in enumerate(saved):

@@ -172,12 +172,19 @@ def test_shade_mc_occlusion_bits_match_oracle(ops, scene):
     args = [cu(sc[k]) for k in ("pts", "nrm", "vd", "features", "features_jitter")]
     rd, rs = cu(sc["rand_d"]).view(-1), cu(sc["rand_s"]).view(-1)
     tab_d, tab_s = cu(ops.direction_tables(200)), cu(ops.direction_tables(128))
-    check(lib().dm_shade_mc_fwd(C.byref(cfg), bvh.h, ptr(env), env.shape[0], env.shape[1], ptr(tab_d), ptr(tab_s),
-                                *[ptr(a) for a in args], ptr(rd), ptr(rs), n, ptr(color), ptr(jac), None,
-                                *([None] * 7), ptr(bits), stream_ptr()), "dm_shade_mc_fwd")
-    b = bits.cpu().numpy().astype(np.uint32)
-    hit_c = ((b[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(n, -1)[:, :328].astype(bool)
-    assert (hit_c != hit_o).mean() < 2e-3
+    perm = cu(ops.sample_order(200, 128))
+    assert sorted(perm.cpu().tolist()) == list(range(328)) and int(perm[:200].max()) < 200
+    colors = []
+    for pm in (None, perm):      # identity order and the direction-coherent order must give the same bits
+        bits.zero_()
+        check(lib().dm_shade_mc_fwd(C.byref(cfg), bvh.h, ptr(env), env.shape[0], env.shape[1], ptr(tab_d), ptr(tab_s),
+                                    *[ptr(a) for a in args], ptr(rd), ptr(rs), n, ptr(color), ptr(jac), None,
+                                    *([None] * 7), ptr(bits), ptr(pm), stream_ptr()), "dm_shade_mc_fwd")
+        b = bits.cpu().numpy().astype(np.uint32)
+        hit_c = ((b[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(n, -1)[:, :328].astype(bool)
+        assert (hit_c != hit_o).mean() < 2e-3
+        colors.append(color.clone())
+    assert rel_err(colors[1].cpu(), colors[0].cpu()) < 1e-5
 
 
 def test_shade_splitsum_forward_backward_match_oracle(ops, scene):
