@@ -76,9 +76,10 @@ struct Builder {
         Box lb, rb;
         int32_t cl = build(first, mid - first, lb);
         int32_t cr = build(mid, first + count - mid, rb);
-        float4 n0 = make_float4(lb.lo[0], lb.lo[1], lb.lo[2], lb.hi[0]);
-        float4 n1 = make_float4(lb.hi[1], lb.hi[2], rb.lo[0], rb.lo[1]);
-        float4 n2 = make_float4(rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]);
+        const float W = 1e-6f;   // pre-widened slabs (see bvh.cuh)
+        float4 n0 = make_float4(lb.lo[0] - W, lb.lo[1] - W, lb.lo[2] - W, lb.hi[0] + W);
+        float4 n1 = make_float4(lb.hi[1] + W, lb.hi[2] + W, rb.lo[0] - W, rb.lo[1] - W);
+        float4 n2 = make_float4(rb.lo[2] - W, rb.hi[0] + W, rb.hi[1] + W, rb.hi[2] + W);
         float4 n3; int32_t z = 0;
         memcpy(&n3.x, &cl, 4); memcpy(&n3.y, &cr, 4); memcpy(&n3.z, &z, 4); memcpy(&n3.w, &z, 4);
         nodes[4 * (size_t)id] = n0; nodes[4 * (size_t)id + 1] = n1; nodes[4 * (size_t)id + 2] = n2; nodes[4 * (size_t)id + 3] = n3;
@@ -112,23 +113,28 @@ extern "C" int dm_bvh_build(const float* verts_host, int64_t n_verts, const int3
         const float* a = verts_host + 3 * (size_t)tris_host[3 * f];
         const float* bb = verts_host + 3 * (size_t)tris_host[3 * f + 1];
         const float* c = verts_host + 3 * (size_t)tris_host[3 * f + 2];
-        float idf; memcpy(&idf, &f, 4);
-        tr[3 * i] = make_float4(a[0], a[1], a[2], idf);
-        tr[3 * i + 1] = make_float4(bb[0], bb[1], bb[2], 0.f);
-        tr[3 * i + 2] = make_float4(c[0], c[1], c[2], 0.f);
+        float e1[3], e2[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = bb[k] - a[k]; e2[k] = c[k] - a[k]; }
+        float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+        tr[3 * i] = make_float4(a[0], a[1], a[2], e1[0]);
+        tr[3 * i + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+        tr[3 * i + 2] = make_float4(e2[2], nx, ny, nz);
     }
     dm_bvh* h = new dm_bvh();
     h->n_nodes = (int32_t)(b.nodes.size() / 4); h->n_tris = (int32_t)n_tris; h->root = rc;
-    h->nodes = nullptr; h->tris = nullptr;
+    h->nodes = nullptr; h->tris = nullptr; h->ids = nullptr;
     size_t nb = std::max<size_t>(b.nodes.size(), 4) * sizeof(float4);
     cudaError_t e = cudaMalloc(&h->nodes, nb);
     if (e == cudaSuccess) e = cudaMalloc(&h->tris, tr.size() * sizeof(float4));
     if (e == cudaSuccess && !b.nodes.empty()) e = cudaMemcpy(h->nodes, b.nodes.data(), b.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->tris, tr.data(), tr.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->ids, sizeof(int32_t) * (size_t)n_tris);
+    if (e == cudaSuccess) e = cudaMemcpy(h->ids, b.leaf_order.data(), sizeof(int32_t) * (size_t)n_tris, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         dm_set_error("dm_bvh_build: %s", cudaGetErrorString(e));
         if (h->nodes) cudaFree(h->nodes);
         if (h->tris) cudaFree(h->tris);
+        if (h->ids) cudaFree(h->ids);
         delete h;
         return (int)e;
     }
@@ -138,7 +144,7 @@ extern "C" int dm_bvh_build(const float* verts_host, int64_t n_verts, const int3
 
 extern "C" void dm_bvh_free(dm_bvh* bvh) {
     if (!bvh) return;
-    cudaFree(bvh->nodes); cudaFree(bvh->tris);
+    cudaFree(bvh->nodes); cudaFree(bvh->tris); cudaFree(bvh->ids);
     delete bvh;
 }
 
@@ -161,7 +167,7 @@ extern "C" int dm_bvh_trace(const dm_bvh* bvh, const float* rays_o, const float*
                             int32_t* tri, float* uv, void* stream) {
     if (n == 0) return DM_OK;
     DM_REQUIRE(bvh && rays_o && rays_d && t && tri, "null pointer");
-    BvhView bv{bvh->nodes, bvh->tris, bvh->root};
+    BvhView bv{bvh->nodes, bvh->tris, bvh->ids, bvh->root};
     bvh_trace_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(bv, rays_o, rays_d, n, t, tri, uv);
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -215,7 +221,7 @@ extern "C" int dm_raster_gbuffer(const dm_bvh* bvh, const float* v_pos, const fl
     if ((int64_t)B * H * W == 0) return DM_OK;
     DM_REQUIRE(bvh && v_pos && v_nrm && tris && rays_o && rays_d && mvp && w2c, "null pointer");
     int64_t n = (int64_t)B * H * W;
-    BvhView bv{bvh->nodes, bvh->tris, bvh->root};
+    BvhView bv{bvh->nodes, bvh->tris, bvh->ids, bvh->root};
     gbuffer_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
         bv, v_pos, v_nrm, tris, rays_o, rays_d, mvp, w2c, B, (int64_t)H * W, rast, gb_pos, gb_nrm, mask, comp_normal);
     DM_CHECK_LAUNCH();

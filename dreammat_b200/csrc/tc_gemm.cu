@@ -19,8 +19,9 @@
 // activation / scale -> 16-byte global stores).  Operand tiles are 128 x 64 (A) and BN x 64 (B)
 // in the 128-byte swizzled K-major layout shared by TMA and the UMMA descriptors; a ring of
 // mbarrier-guarded stages feeds the tensor core, tcgen05.commit releases stages and signals the
-// epilogue.  Two CTAs fit per SM (<= 99 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
-// overlaps the other's main loop.
+// epilogue.  The kernel is persistent (one CTA per SM walks a strided list of tiles) with a double-buffered
+// TMEM accumulator, so the epilogue of tile i overlaps the main loop of tile i+1 and the TMA ring never drains
+// at tile boundaries.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -63,34 +64,42 @@ template <int BN> struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
+    // persistent CTA, one per SM: ~192 KB of operand ring
+    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int ACC_STAGES = 2;                       // TMEM accumulator double buffer
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
 };
 
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// The TMA producer runs ahead across tile boundaries, the MMA warp alternates between two TMEM accumulators and the
+// epilogue warps drain accumulator i while the tensor pipe already works on accumulator i^1.
 template <int BN, typename T>
-__global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           const GemmParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const GemmParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
-    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address word
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y, z = blockIdx.z;
     const int nk = p.K / BK;
+    const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM - 1) / BM;
+    const int tiles_per_z = n_tiles * m_tiles;
+    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -102,30 +111,34 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer
-            int c_n = 0, c_h = 0, c_w = 0;
-            if (p.is_conv) {
-                int tiles_w = p.Wo / p.tile_w, tiles_h = p.Ho / p.tile_h;
-                int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
-                c_w = tw * p.tile_w * p.stride - p.pad_l;
-                c_h = th * p.tile_h * p.stride - p.pad_t;
-                c_n = tn * p.tile_n;
-            }
             const int slabs = p.is_conv ? (p.Cin / BK) : nk;
+            const int tiles_w = p.is_conv ? p.Wo / p.tile_w : 1, tiles_h = p.is_conv ? p.Ho / p.tile_h : 1;
             int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < nk; ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-                const uint32_t b_dst = a_dst + C::A_BYTES;
-                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+                const int m_tile = r / n_tiles, n_tile = r - m_tile * n_tiles;
+                int c_n = 0, c_h = 0, c_w = 0;
                 if (p.is_conv) {
-                    int tap = kb / slabs, slab = kb - tap * slabs;
-                    int kh = tap / p.kw_n, kw = tap - kh * p.kw_n;
-                    tma_load_4d(a_dst, &tmA, full_bar(stage), slab * BK, c_w + kw, c_h + kh, c_n);
-                } else {
-                    tma_load_3d(a_dst, &tmA, full_bar(stage), kb * BK, m_tile * BM, z);
+                    int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
+                    c_w = tw * p.tile_w * p.stride - p.pad_l;
+                    c_h = th * p.tile_h * p.stride - p.pad_t;
+                    c_n = tn * p.tile_n;
                 }
-                tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, p.b_batched ? z : 0);
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + C::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    if (p.is_conv) {
+                        int tap = kb / slabs, slab = kb - tap * slabs;
+                        int kh = tap / p.kw_n, kw = tap - kh * p.kw_n;
+                        tma_load_4d(a_dst, &tmA, full_bar(stage), slab * BK, c_w + kw, c_h + kh, c_n);
+                    } else {
+                        tma_load_3d(a_dst, &tmA, full_bar(stage), kb * BK, m_tile * BM, z);
+                    }
+                    tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, p.b_batched ? z : 0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -135,101 +148,121 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
             constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
                                        ((uint32_t)(BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < nk; ++kb) {
-                mbar_wait(full_bar(stage), phase);
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
-                const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + C::A_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + C::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // +32 bytes along K inside the 128-byte swizzle atom = +2 in the (addr >> 4) field
-                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes along K inside the 128-byte swizzle atom = +2 in the (addr >> 4) field
+                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(empty_bar(stage));
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                umma_commit(tmem_full_bar(acc));
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
         // ---------------------------------------------------- epilogue warps 2..5
         const int quarter = warp & 3;           // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;    // row inside the tile
-        const int64_t m = (int64_t)m_tile * BM + row;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const bool row_ok = m < p.M;
         const T* bias = (const T*)p.bias;
-        const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
-        const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
-        char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int z = t / tiles_per_z, r_ = t - z * tiles_per_z;
+            const int m_tile = r_ / n_tiles, n_tile = r_ - m_tile * n_tiles;
+            const int64_t m = (int64_t)m_tile * BM + row;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const bool row_ok = m < p.M;
+            const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
+            const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
+            char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            const int n0 = n_tile * BN + c0;
-            if (!row_ok || n0 >= p.N) continue;
-            float f[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {
+                    // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                }
+                const int n0 = n_tile * BN + c0;
+                if (!row_ok || n0 >= p.N) continue;
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-            const bool full = (n0 + 32 <= p.N);
-            if (bias) {
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                const bool full = (n0 + 32 <= p.N);
+                if (bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(bias[n0 + j]);
-            }
-            if (rowvec) {
+                    for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(bias[n0 + j]);
+                }
+                if (rowvec) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(rowvec[n0 + j]);
-            }
-            if (p.act == 1) {
+                    for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(rowvec[n0 + j]);
+                }
+                if (p.act == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
-            } else if (p.act == 2) {
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                } else if (p.act == 2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
-            }
-            if (res) {
-                if (full && ((p.ld_res & 7) == 0)) {
-                    const uint4* r4 = reinterpret_cast<const uint4*>(res + n0);
+                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+                }
+                if (res) {
+                    if (full && ((p.ld_res & 7) == 0)) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(res + n0);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u = r4[q];
-                        const T* h = reinterpret_cast<const T*>(&u);
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u = r4[q];
+                            const T* h = reinterpret_cast<const T*>(&u);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[q * 8 + j] += Cvt<T>::to_f(h[j]);
+                            for (int j = 0; j < 8; ++j) f[q * 8 + j] += Cvt<T>::to_f(h[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += Cvt<T>::to_f(res[n0 + j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(outp) + n0;
+                    if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = f[j];
                     }
                 } else {
+                    T* o = reinterpret_cast<T*>(outp) + n0;
+                    if (full && ((p.ldc & 7) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += Cvt<T>::to_f(res[n0 + j]);
-                }
-            }
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            T* h = reinterpret_cast<T*>(&u);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
-            if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(outp) + n0;
-                if (full && ((p.ldc & 3) == 0)) {
+                            for (int j = 0; j < 8; ++j) h[j] = Cvt<T>::from_f(f[q * 8 + j]);
+                            reinterpret_cast<uint4*>(o)[q] = u;
+                        }
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = f[j];
-                }
-            } else {
-                T* o = reinterpret_cast<T*>(outp) + n0;
-                if (full && ((p.ldc & 7) == 0)) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        T* h = reinterpret_cast<T*>(&u);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) h[j] = Cvt<T>::from_f(f[q * 8 + j]);
-                        reinterpret_cast<uint4*>(o)[q] = u;
+                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = Cvt<T>::from_f(f[j]);
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = Cvt<T>::from_f(f[j]);
                 }
             }
+            if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
     }
     tc_fence_before();
@@ -283,7 +316,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         configured = true;
     }
-    dim3 grid((unsigned)dm_ceil_div(p.N, BN), (unsigned)dm_ceil_div(p.M, BM), (unsigned)(p.batch > 0 ? p.batch : 1));
+    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1);
+    unsigned grid = (unsigned)(tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS);   // persistent: one CTA per SM
     kern<<<grid, NTHREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, p);
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -306,9 +340,9 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p
 int pick_bn(int64_t M, int N, int bn_hint) {
     if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
     if (N <= 64) return 64;
-    // too few 128x128 tiles to fill 148 SMs x 2 resident CTAs: halve the tile width (low-resolution UNet levels)
+    // fewer 128x128 tiles than SMs: halve the tile width so every SM gets work (low-resolution UNet levels)
     int64_t tiles128 = dm_ceil_div(M, BM) * dm_ceil_div(N, 128);
-    if (tiles128 < (int64_t)DM_NUM_SMS * 3 / 2) return 64;
+    if (tiles128 < (int64_t)DM_NUM_SMS && N % 64 == 0) return 64;
     if (N % 128 == 0) return 128;
     if (N % 64 == 0 && N < 512) return 64;
     return 128;
