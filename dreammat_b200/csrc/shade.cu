@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
                         }
                     }
                 }
-                if (slot < S) {
+                while (slot < S) {
                     // ---- next sample of this lane: direction (value and d/da), :554-596
                     int s = P.perm ? P.perm[slot] : slot;
                     slot += 32;
@@ -256,12 +256,17 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
                         d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
                         d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
                     }
+                    // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless
+                    // the aux light maps are requested its radiance is never used, so the ray need not be traced
+                    if (spec && !P.spec_light && !P.hit_bits &&
+                        (d.x.v * px.n[0] + d.y.v * px.n[1] + d.z.v * px.n[2]) <= 0.0f) continue;
                     // occlusion ray from p + 1e-5 d (:493-494)
                     ro = mk3(px.p[0] + d.x.v * 1e-5f, px.p[1] + d.y.v * 1e-5f, px.p[2] + d.z.v * 1e-5f);
                     rinv = mk3(1.0f / d.x.v, 1.0f / d.y.v, 1.0f / d.z.v);
                     roi = mk3(ro.x * rinv.x, ro.y * rinv.y, ro.z * rinv.z);
                     cur = P.bvh.root; sp = 0;
                     have = true;
+                    break;
                 }
             }
             unsigned busy = __ballot_sync(0xffffffffu, have);
