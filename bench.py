@@ -112,6 +112,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(device))
     from dreammat_b200 import _cabi
     _cabi.check(_cabi.lib().dm_device_check(local), "dm_device_check")   # fails loudly without the sm_100a library

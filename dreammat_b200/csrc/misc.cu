@@ -130,6 +130,26 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     if (i < tail) upd(pt[i], gt[i], mt[i], vt[i]);
 }
 
+// silhouette antialias as a cached sparse blend (see dreammat_b200/antialias.py): out[dst] += a * (in[src] - in[dst])
+__global__ void aa_fwd_kernel(const float* __restrict__ in, const int32_t* __restrict__ dst, const int32_t* __restrict__ src,
+                              const float* __restrict__ alpha, int64_t k, int c, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * c) return;
+    int64_t e = i / c; int ch = (int)(i - e * c);
+    int64_t d = dst[e], s_ = src[e];
+    atomicAdd(out + d * c + ch, alpha[e] * (in[s_ * c + ch] - in[d * c + ch]));
+}
+__global__ void aa_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ dst, const int32_t* __restrict__ src,
+                              const float* __restrict__ alpha, int64_t k, int c, float* __restrict__ din) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * c) return;
+    int64_t e = i / c; int ch = (int)(i - e * c);
+    int64_t d = dst[e], s_ = src[e];
+    float g = alpha[e] * dout[d * c + ch];
+    atomicAdd(din + s_ * c + ch, g);
+    atomicAdd(din + d * c + ch, -g);
+}
+
 // CSD combine (dreammat_guidance.py:475-481, 584-594) with the 10 diagnostic sums.
 __global__ void __launch_bounds__(256) sds_kernel(const float* __restrict__ e, const float* __restrict__ noise,
                                                   const float* __restrict__ w, int B, int64_t chw, float ct, float cu,
@@ -216,6 +236,30 @@ extern "C" int dm_fill(float* p, int64_t n, float v, void* stream) {
     if (n == 0) return DM_OK;
     DM_REQUIRE(p, "null pointer");
     fill_kernel<<<(unsigned)dm_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_antialias_fwd(const float* in, const int32_t* dst, const int32_t* src, const float* alpha, int64_t k,
+                                int64_t n_pix, int c, float* out, void* stream) {
+    DM_REQUIRE(in && out && c > 0, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in != out) DM_CHECK_CUDA(cudaMemcpyAsync(out, in, sizeof(float) * n_pix * c, cudaMemcpyDeviceToDevice, st));
+    if (k == 0) return DM_OK;
+    DM_REQUIRE(dst && src && alpha && in != out, "null pointer / in-place with pairs");
+    aa_fwd_kernel<<<(unsigned)dm_ceil_div(k * c, 256), 256, 0, st>>>(in, dst, src, alpha, k, c, out);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_antialias_bwd(const float* dout, const int32_t* dst, const int32_t* src, const float* alpha, int64_t k,
+                                int64_t n_pix, int c, float* din, void* stream) {
+    DM_REQUIRE(dout && din && c > 0 && dout != din, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CHECK_CUDA(cudaMemcpyAsync(din, dout, sizeof(float) * n_pix * c, cudaMemcpyDeviceToDevice, st));
+    if (k == 0) return DM_OK;
+    DM_REQUIRE(dst && src && alpha, "null pointer");
+    aa_bwd_kernel<<<(unsigned)dm_ceil_div(k * c, 256), 256, 0, st>>>(dout, dst, src, alpha, k, c, din);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

@@ -13,8 +13,8 @@ per-iteration path is a C-ABI kernel launch.  B200-first departures (all result-
   * `DreamMat.training_step_fused` runs the iteration as an explicit forward/backward kernel sequence with
     one flat gradient buffer (what the multi-GPU all-reduce and the fused Adam operate on) instead of a
     torch autograd graph; `forward()` + autograd wrappers remain for API parity.
-The silhouette antialias pass (dr.antialias, raytracing_renderer.py:127,147,199) is not implemented yet:
-comp_rgb differs from the reference on silhouette pixels only (out-of-scope list).
+  * the silhouette antialias pass (dr.antialias, raytracing_renderer.py:127,147,199) depends only on the fixed
+    G-buffer, so its (dst, src, weight) pair list is built once per view and applied as a sparse blend.
 """
 from __future__ import annotations
 
@@ -25,6 +25,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
+from . import antialias as AA
 from . import render_ops as R
 from ._cabi import MaterialCfg, check, lib, ptr, stream_ptr
 from .scene import normalize_mesh, load_obj, vertex_normals
@@ -198,6 +199,9 @@ class RaytraceRender:
         self.tris_d = self.mesh.t_pos_idx.to(self.device)
         self.change_eps = 0.05
         self._cache: Dict[int, dict] = {}
+        self._faces_np = self.mesh.t_pos_idx.numpy().astype(np.int64)
+        self._vpos_np = self.mesh.v_pos.numpy()
+        self._nbr_opp = AA.edge_neighbours(self._faces_np, self._vpos_np.shape[0])
 
     def gbuffer(self, rays_o, rays_d, mvp_mtx, w2c, key: Optional[int] = None):
         """raytracing_renderer.py:122-159 for ONE view; cached under `key` (fixed view id)."""
@@ -209,10 +213,16 @@ class RaytraceRender:
             w2c.to(dev))
         pix = R.compact_mask(mask)
         vd = (-rays_d.to(dev)).reshape(-1, 3).contiguous()
+        # antialias pair list of this view (host, once): raytracing_renderer.py:127,147,199
+        d_, s_, a_ = AA.build_pairs(rast[0].cpu().numpy(), self._vpos_np, self._faces_np, self._nbr_opp,
+                                    mvp_mtx[0].detach().cpu().numpy())
+        aa = (torch.from_numpy(d_).to(dev), torch.from_numpy(s_).to(dev), torch.from_numpy(a_).to(dev))
+        Hh, Ww = rast.shape[1], rast.shape[2]
         g = {"pix": pix, "pn": int(pix.shape[0]), "pts": R.gather_rows(gb_pos.view(-1, 3), pix),
-             "nrm": R.gather_rows(gb_nrm.view(-1, 3), pix), "vd": R.gather_rows(vd, pix),
-             "comp_depth": R.depth_normalize(rast, mask).view(1, *rast.shape[1:3], 1), "comp_normal": comp_normal,
-             "opacity": mask.view(1, *rast.shape[1:3], 1).float()}
+             "nrm": R.gather_rows(gb_nrm.view(-1, 3), pix), "vd": R.gather_rows(vd, pix), "aa": aa,
+             "comp_depth": R.depth_normalize(rast, mask).view(1, Hh, Ww, 1),
+             "comp_normal": AA.antialias(comp_normal.view(-1, 3), aa).view(1, Hh, Ww, 3),
+             "opacity": AA.antialias(mask.view(-1, 1).float(), aa).view(1, Hh, Ww, 1)}
         if key is not None:
             self._cache[key] = g
         return g
@@ -238,7 +248,7 @@ class RaytraceRender:
             fj = R.hashgrid_mlp(pj, grid, geo.W1, geo.W2, geo.hg)
             so, reg = self.material(g["pts"], f, fj, g["vd"], g["nrm"], env_id[b], reg_weight_n=total)
             regs.append(reg)
-            canv = {"comp_rgb": R.scatter_canvas(so["color"], g["pix"], H * W).view(1, H, W, 3)}
+            canv = {"comp_rgb": AA.antialias(R.scatter_canvas(so["color"], g["pix"], H * W), g["aa"]).view(1, H, W, 3)}
             for k_out, k_in, c in (("albedo", "albedo", 3), ("metalness", "metalness", 1), ("roughness", "roughness", 1),
                                    ("specular_light", "specular_lights", 3), ("diffuse_light", "diffuse_lights", 3),
                                    ("specular_color", "specular_colors", 3), ("diffuse_color", "diffuse_colors", 3)):
@@ -335,7 +345,8 @@ class DreamMat:
         total_pn = total_pn_global or sum(g["pn"] for g in gbs)
         g_ = getattr(guid, "graphs", None)
         canvas = g_.rgb.view(B, H * W, 3) if (g_ is not None and g_.B == B and rng is None) else torch.empty(B, H * W, 3, device=dev)
-        check(lib().dm_fill(ptr(canvas), canvas.numel(), 1.0, st), "dm_fill")
+        raw = torch.empty(B, H * W, 3, device=dev)            # canvas before the antialias blend
+        check(lib().dm_fill(ptr(raw), raw.numel(), 1.0, st), "dm_fill")
         reg_sums = torch.zeros(2, device=dev)
         saved = []
         for b, g in enumerate(gbs):
@@ -355,7 +366,11 @@ class DreamMat:
                                         ptr(mat.tab_d), ptr(mat.tab_s), ptr(g["pts"]), ptr(g["nrm"]), ptr(g["vd"]), ptr(f),
                                         ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
                                         None, ptr(mat.perm), st), "dm_shade_mc_fwd")
-            check(lib().dm_scatter_canvas(ptr(color), ptr(g["pix"]), n, 3, ptr(canvas[b]), st), "dm_scatter_canvas")
+            check(lib().dm_scatter_canvas(ptr(color), ptr(g["pix"]), n, 3, ptr(raw[b]), st), "dm_scatter_canvas")
+            aa = g.get("aa")
+            k_aa = int(aa[0].shape[0]) if aa is not None else 0
+            check(lib().dm_antialias_fwd(ptr(raw[b]), ptr(aa[0]) if k_aa else None, ptr(aa[1]) if k_aa else None,
+                                         ptr(aa[2]) if k_aa else None, k_aa, H * W, 3, ptr(canvas[b]), st), "dm_antialias_fwd")
             saved.append((g, pj, f, fj, jac))
         use_graphs = getattr(guid, "graphs", None) is not None and guid.graphs.B == B and rng is None
         comp_rgb = canvas.view(B, H, W, 3)
@@ -386,7 +401,12 @@ class DreamMat:
         for b, (g, pj, f, fj, jac) in enumerate(saved):
             n = g["pn"]
             dcolor = torch.empty(n, 3, device=dev)
-            check(lib().dm_gather_canvas_grad(ptr(dcanvas[b]), ptr(g["pix"]), n, 3, ptr(dcolor), st), "gather")
+            aa = g.get("aa")
+            k_aa = int(aa[0].shape[0]) if aa is not None else 0
+            draw = torch.empty(H * W, 3, device=dev)
+            check(lib().dm_antialias_bwd(ptr(dcanvas[b]), ptr(aa[0]) if k_aa else None, ptr(aa[1]) if k_aa else None,
+                                         ptr(aa[2]) if k_aa else None, k_aa, H * W, 3, ptr(draw), st), "dm_antialias_bwd")
+            check(lib().dm_gather_canvas_grad(ptr(draw), ptr(g["pix"]), n, 3, ptr(dcolor), st), "gather")
             df = torch.empty(n, 5, device=dev); dfj = torch.empty(n, 5, device=dev)
             check(lib().dm_shade_bwd(C.byref(mat.mc_cfg), ptr(f), ptr(fj), ptr(dcolor), ptr(jac), lam_reg * 0.25 / total_pn,
                                      lam_reg * 0.1 / total_pn, n, ptr(df), ptr(dfj), st), "dm_shade_bwd")

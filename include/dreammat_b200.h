@@ -144,6 +144,14 @@ int dm_fill(float* p, int64_t n, float v, void* stream);
 /* dvalues[i,:] = dcanvas[pix[i],:] */
 int dm_gather_canvas_grad(const float* dcanvas, const int32_t* pix, int64_t n, int c, float* dvalues, void* stream);
 
+/* silhouette antialias (dr.antialias, utils/rasterize.py:56 <- raytracing_renderer.py:127,147,199) as a sparse
+ * blend whose pair list (dst pixel, src pixel, weight) is fixed per view and built once on the host
+ * (dreammat_b200/antialias.py): out = in; out[dst[k]] += alpha[k] * (in[src[k]] - in[dst[k]]).  bwd is its adjoint. */
+int dm_antialias_fwd(const float* in, const int32_t* dst, const int32_t* src, const float* alpha, int64_t k,
+                     int64_t n_pix, int c, float* out, void* stream);
+int dm_antialias_bwd(const float* dout, const int32_t* dst, const int32_t* src, const float* alpha, int64_t k,
+                     int64_t n_pix, int c, float* din, void* stream);
+
 /* ------------------------------------------------------------------ optimiser (a9)
  * torch.optim.Adam as configured by systems/utils.py:34-53 + configs/dreammat.yaml:110-115 */
 int dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -742,3 +742,90 @@ def synthetic_envmap(H=256, W=512, seed=0):
     img = img + sun[..., None] * torch.tensor([1.0, 0.9, 0.7])
     img = img * (0.9 + 0.2 * torch.rand(H, W, 1, generator=g))
     return img.contiguous()
+
+
+# ----------------------------------------------------------------------------- antialias (K3)
+
+
+def antialias_pairs(rast, v_pos, faces, mvp):
+    """Scalar restatement of nvdiffrast's antialias analysis (un-vendored; Laine et al. 2020 sec. 3.4) for ONE view.
+
+    rast [H,W,4] = (u, v, z/w, tri+1).  Returns a list of (dst_pixel, src_pixel, weight): out[dst] += w*(in[src]-in[dst]).
+    For each adjacent pixel pair with different triangle ids: take the front triangle (smaller z/w, or the only one);
+    among its silhouette edges (boundary, or the neighbouring triangle's opposite vertex lies on the same side of the
+    edge in screen space) that cross the segment between the pixel centres, take the nearest crossing s in [0,1]
+    measured from the front triangle's pixel; s > 0.5 blends into the other pixel with s-0.5, s < 0.5 into its own
+    pixel with 0.5-s."""
+    H, W, _ = rast.shape
+    V = v_pos.shape[0]
+    clip = torch.cat([v_pos, torch.ones(V, 1)], 1) @ mvp.t()
+    sx = (clip[:, 0] / clip[:, 3] * 0.5 + 0.5) * W
+    sy = (clip[:, 1] / clip[:, 3] * 0.5 + 0.5) * H
+    f = faces.long().tolist()
+    edge_map = {}
+    for fi, (a, b, c) in enumerate(f):
+        for (p, q, o) in ((a, b, c), (b, c, a), (c, a, b)):
+            edge_map.setdefault((min(p, q), max(p, q)), []).append((fi, o))
+    tri = (rast[..., 3].long() - 1).tolist()
+    zw = rast[..., 2].tolist()
+    sxl, syl = sx.tolist(), sy.tolist()
+    out = []
+    for y in range(H):
+        for x in range(W):
+            for (dy, dx) in ((0, 1), (1, 0)):
+                y1, x1 = y + dy, x + dx
+                if y1 >= H or x1 >= W:
+                    continue
+                t0, t1 = tri[y][x], tri[y1][x1]
+                if t0 == t1:
+                    continue
+                if t0 < 0:
+                    first = False
+                elif t1 < 0:
+                    first = True
+                else:
+                    first = zw[y][x] < zw[y1][x1]
+                T = t0 if first else t1
+                (cy, cx), (oy, ox) = ((y, x), (y1, x1)) if first else ((y1, x1), (y, x))
+                sgn = 1.0 if first else -1.0
+                ccx, ccy = cx + 0.5, cy + 0.5
+                a, b, c = f[T]
+                best = None
+                for (p, q, o3) in ((a, b, c), (b, c, a), (c, a, b)):
+                    others = [o for (fi, o) in edge_map[(min(p, q), max(p, q))] if fi != T]
+                    ex, ey = sxl[q] - sxl[p], syl[q] - syl[p]
+                    side_c = ex * (syl[o3] - syl[p]) - ey * (sxl[o3] - sxl[p])
+                    if others:
+                        oo = others[0]
+                        side_o = ex * (syl[oo] - syl[p]) - ey * (sxl[oo] - sxl[p])
+                        sil = side_o * side_c > 0
+                    else:
+                        sil = True
+                    if not sil:
+                        continue
+                    if dx == 1:
+                        da, db = syl[p] - ccy, syl[q] - ccy
+                        if not da * db < 0:
+                            continue
+                        s = (sxl[p] + ex * (da / (da - db)) - ccx) * sgn
+                    else:
+                        da, db = sxl[p] - ccx, sxl[q] - ccx
+                        if not da * db < 0:
+                            continue
+                        s = (syl[p] + ey * (da / (da - db)) - ccy) * sgn
+                    if 0 <= s <= 1 and (best is None or s < best):
+                        best = s
+                if best is None or best == 0.5:
+                    continue
+                ci, oi = cy * W + cx, oy * W + ox
+                out.append((oi, ci, best - 0.5) if best > 0.5 else (ci, oi, 0.5 - best))
+    return out
+
+
+def antialias_apply(x, pairs):
+    """x [n_pix, c] -> blended copy (differentiable)."""
+    if not pairs:
+        return x.clone()
+    dst = torch.tensor([p[0] for p in pairs]); src = torch.tensor([p[1] for p in pairs])
+    w = torch.tensor([p[2] for p in pairs], dtype=x.dtype)[:, None]
+    return x.index_add(0, dst, w * (x[src] - x[dst]))

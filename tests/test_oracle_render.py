@@ -143,3 +143,27 @@ def test_gbuffer_and_jitter_shapes():
     pj = O.jitter_positions(sc["pts"], sc["nrm"], sc["rand_ang"], sc["normal_eps"])
     off = pj - sc["pts"]
     assert float((off * sc["nrm"]).sum(-1).abs().max()) < 1e-5  # stays in the tangent plane
+
+
+def test_antialias_pairs_product_host_code_matches_oracle():
+    """The cached silhouette-blend list (dreammat_b200/antialias.py, vectorised numpy, init-time host code) against the
+    oracle's scalar restatement; and the blend is a partition-of-unity operation."""
+    from dreammat_b200 import antialias as A
+    sc = make_scene(res=40, subdiv=2, bump=0.15, seed=1, n_views=2)
+    nbr = A.edge_neighbours(sc["f"].numpy().astype(np.int64), sc["v"].shape[0])
+    assert (nbr >= 0).all()          # closed mesh: every edge has a neighbour
+    for b in range(2):
+        rast = sc["gb"]["rast"][b]
+        pairs = O.antialias_pairs(rast, sc["v"], sc["f"], sc["cam"]["mvp_mtx"][b])
+        d, s, a = A.build_pairs(rast.numpy(), sc["v"].numpy(), sc["f"].numpy().astype(np.int64), nbr,
+                                sc["cam"]["mvp_mtx"][b].numpy())
+        po = sorted((p[0], p[1], round(p[2], 4)) for p in pairs)
+        pp = sorted((int(x), int(y), round(float(z), 4)) for x, y, z in zip(d, s, a))
+        assert po == pp and len(po) > 20
+        assert 0 < min(p[2] for p in pairs) and max(p[2] for p in pairs) <= 0.5
+        x = torch.full((40 * 40, 3), 0.7)
+        assert float((O.antialias_apply(x, pairs) - x).abs().max()) < 1e-6   # constant images are fixed points
+        # the mask gets fractional coverage on both sides of the silhouette
+        m = sc["gb"]["mask"][b].reshape(-1, 1).float()
+        ma = O.antialias_apply(m, pairs)
+        assert ((ma > 0.01) & (ma < 0.99)).sum() > 20
