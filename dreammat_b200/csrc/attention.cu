@@ -48,6 +48,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (64ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <typename T> struct PK;
 template <> struct PK<__half> {
     static __device__ __forceinline__ uint32_t pack(float a, float b) {
@@ -166,20 +172,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
                 for (int c = 0; c < 32; ++c) { sv[c] = t0[c]; sv[32 + c] = t1[c]; }
             }
             const int kvalid = p.Nk - j * AK;  // keys of this block that exist
-            float mx = m_run;
+            float mraw = -INFINITY;
+            if (kvalid >= AK) {
 #pragma unroll
-            for (int c = 0; c < AK; ++c) {
-                float s = __uint_as_float(sv[c]) * p.scale_log2e;
-                s = (c < kvalid) ? s : -INFINITY;
-                sv[c] = __float_as_uint(s);
-                mx = fmaxf(mx, s);
+                for (int c = 0; c < AK; ++c) mraw = fmaxf(mraw, __uint_as_float(sv[c]));
+            } else {            // ragged last block (cross-attention over 77 tokens): mask the missing keys
+#pragma unroll
+                for (int c = 0; c < AK; ++c) {
+                    float s = (c < kvalid) ? __uint_as_float(sv[c]) : -INFINITY;
+                    sv[c] = __float_as_uint(s);
+                    mraw = fmaxf(mraw, s);
+                }
             }
-            const float alpha = exp2f(m_run - mx);   // m_run = -inf on the first block -> 0
+            const float mx = fmaxf(m_run, mraw * p.scale_log2e);   // running max in the scaled (log2) domain
+            const float alpha = fast_exp2(m_run - mx);             // m_run = -inf on the first block -> 0
+            const float neg_mx = -mx;
             float lsum = 0.f;
             uint32_t pk[32];
 #pragma unroll
             for (int c = 0; c < AK; c += 2) {
-                float p0 = exp2f(__uint_as_float(sv[c]) - mx), p1 = exp2f(__uint_as_float(sv[c + 1]) - mx);
+                // one FFMA + one MUFU.EX2 per element: exp2(s * scale*log2e - max)
+                float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2e, neg_mx));
+                float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2e, neg_mx));
                 lsum += p0 + p1;
                 pk[c >> 1] = PK<T>::pack(p0, p1);
             }

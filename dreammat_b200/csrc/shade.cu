@@ -107,6 +107,7 @@ struct McParams {
     float *color, *jac, *reg_sums;
     float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
     uint32_t* hit_bits;
+    int refill_below, leaf_batch, skip_horizon;   // traversal scheduling knobs (dm_tune)
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
@@ -177,8 +178,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
         // state machine (set up a ray -> traverse step by step -> finalise), and the warp only leaves the
         // traversal loop to finalise / refill when fewer than REFILL_BELOW lanes still have a ray in flight
         // (Aila-Laine style persistent rays; keeps SIMT efficiency high in both phases).
-        constexpr int REFILL_BELOW = 20;
-        constexpr int LEAF_BATCH = 12;
+        const int REFILL_BELOW = P.refill_below, LEAF_BATCH = P.leaf_batch;
         int slot = lane;
         bool have = false, pending = false, hit = false, spec = false;
         int s_cur = 0;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
                     }
                     // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless
                     // the aux light maps are requested its radiance is never used, so the ray need not be traced
-                    if (spec && !P.spec_light && !P.hit_bits &&
+                    if (P.skip_horizon && spec && !P.spec_light && !P.hit_bits &&
                         (d.x.v * px.n[0] + d.y.v * px.n[1] + d.z.v * px.n[2]) <= 0.0f) continue;
                     // occlusion ray from p + 1e-5 d (:493-494)
                     ro = mk3(px.p[0] + d.x.v * 1e-5f, px.p[1] + d.y.v * 1e-5f, px.p[2] + d.z.v * 1e-5f);
@@ -559,6 +559,18 @@ __global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, flo
 
 }  // namespace
 
+static int g_mc_refill = 20, g_mc_leaf_batch = 12, g_mc_skip_horizon = 1;
+
+/* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
+extern "C" int dm_tune(const char* key, int value) {
+    if (!key) return DM_EINVAL;
+    if (!strcmp(key, "mc_refill")) g_mc_refill = value;
+    else if (!strcmp(key, "mc_leaf_batch")) g_mc_leaf_batch = value;
+    else if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    else { dm_set_error("dm_tune: unknown key %s", key); return DM_EINVAL; }
+    return DM_OK;
+}
+
 extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, const float* env_rgba, int envH, int envW,
                                const float* tab_d, const float* tab_s, const float* pts, const float* normals,
                                const float* viewdirs, const float* features, const float* features_jitter,
@@ -577,6 +589,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.rand_d = rand_d; P.rand_s = rand_s; P.n = n; P.color = color; P.jac = jac; P.reg_sums = reg_sums;
     P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
+    P.refill_below = g_mc_refill; P.leaf_batch = g_mc_leaf_batch; P.skip_horizon = g_mc_skip_horizon;
     size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float);
     shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();

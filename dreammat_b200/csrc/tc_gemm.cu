@@ -60,12 +60,14 @@ template <> struct Cvt<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
-template <int BN> struct Cfg {
+// CPS = persistent CTAs per SM.  Two co-resident CTAs (each with its own single-thread MMA issuer and a ~96 KB operand
+// ring) keep the tensor pipe's queue fuller for the narrower tiles; 256-wide tiles need all of TMEM and run one per SM.
+template <int BN, int CPS> struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // persistent CTA, one per SM: ~192 KB of operand ring
-    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int RING = (CPS == 1) ? 196608 : 98304;
+    static constexpr int STAGES = RING / STAGE_BYTES;
     static constexpr int ACC_STAGES = 2;                       // TMEM accumulator double buffer
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
@@ -74,11 +76,11 @@ template <int BN> struct Cfg {
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // The TMA producer runs ahead across tile boundaries, the MMA warp alternates between two TMEM accumulators and the
 // epilogue warps drain accumulator i while the tensor pipe already works on accumulator i^1.
-template <int BN, typename T>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, typename T, int CPS>
+__global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CPS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -308,19 +310,30 @@ int encode_map(CUtensorMap* m, int bf16, const void* base, int rank, const uint6
     return DM_OK;
 }
 
-template <int BN, typename T>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+int g_gemm_cps = 2;   // persistent CTAs per SM for BN <= 128 (dm_tune "gemm_cps")
+
+template <int BN, typename T, int CPS>
+int launch_cps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_gemm_kernel<BN, T>;
+    auto kern = tc_gemm_kernel<BN, T, CPS>;
     if (!configured) {
-        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CPS>::SMEM));
         configured = true;
     }
     int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1);
-    unsigned grid = (unsigned)(tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS);   // persistent: one CTA per SM
-    kern<<<grid, NTHREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    int64_t slots = (int64_t)DM_NUM_SMS * CPS;
+    unsigned grid = (unsigned)(tiles < slots ? tiles : slots);   // persistent: CPS CTAs per SM
+    kern<<<grid, NTHREADS, Cfg<BN, CPS>::SMEM, st>>>(tmA, tmB, p);
     DM_CHECK_LAUNCH();
     return DM_OK;
+}
+
+template <int BN, typename T>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+    if constexpr (BN <= 128) {
+        if (g_gemm_cps == 2) return launch_cps<BN, T, 2>(tmA, tmB, p, st);
+    }
+    return launch_cps<BN, T, 1>(tmA, tmB, p, st);
 }
 
 int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st) {
@@ -366,6 +379,8 @@ void fill_epilogue(GemmParams& p, const dm_epilogue* e, int N) {
 }
 
 }  // namespace
+
+extern "C" int dm_tune_gemm(int ctas_per_sm) { g_gemm_cps = ctas_per_sm == 1 ? 1 : 2; return DM_OK; }
 
 extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
                        int64_t b_batch_stride, void* C, int64_t ldc, int64_t c_batch_stride, int M, int N, int K,

@@ -29,6 +29,9 @@ extern "C" {
 
 const char* dm_last_error(void);
 int dm_version(void);
+/* scheduling knobs for experiments: "mc_refill", "mc_leaf_batch", "mc_skip_horizon" */
+int dm_tune(const char* key, int value);
+int dm_tune_gemm(int ctas_per_sm);   /* persistent CTAs per SM for tiles <= 128 wide (1 or 2) */
 /* number of kernels this library has launched in the process (bench.py's gpu_launches) */
 long long dm_launch_count(void);
 /* device sanity: returns 0 iff device `dev` is compute capability 10.x (sm_100a code present). */

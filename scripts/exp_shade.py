@@ -11,13 +11,18 @@ geo = DreamMatMesh({"shape_init": "p"}, dev, mesh=mesh)
 mat = DreamMatMaterial({"diffuse_sample_num": 200, "specular_sample_num": 128}, dev, [synthetic_envmap(2048, 4096, 0)])
 ren = RaytraceRender({}, geo, mat, None, dev)
 cams = FixCameraSet(DataConfig(width=512, height=512), torch.Generator().manual_seed(0))
-for vid in (3, 40):
+for vid in (3,):
     c = cams.cameras(torch.tensor([vid]))
     g = ren.gbuffer(c["rays_o"].to(dev), c["rays_d"].to(dev), c["mvp_mtx"].to(dev), c["w2c"].to(dev), vid)
     n = g["pn"]
     f = torch.randn(n, 5, device=dev); fj = torch.randn(n, 5, device=dev)
     rd, rs = torch.rand(n, device=dev), torch.rand(n, device=dev)
-    for name, pm in (("identity order", None), ("morton order", mat.perm)):
+    from dreammat_b200._cabi import lib
+    variants = [(f"refill{r} leaf{l}", r, l, 1) for (r, l) in ((1, 1), (1, 8), (2, 4), (4, 1), (4, 8), (6, 8), (8, 1), (8, 4), (8, 8),
+                                                                    (8, 16), (12, 8), (12, 1))] + [("M refill4 leaf8", 4, 8, 1), ("M refill1 leaf1", 1, 1, 1), ("M refill8 leaf8", 8, 8, 1)]
+    for name, rf, lb, sk in variants:
+        lib().dm_tune(b"mc_refill", rf); lib().dm_tune(b"mc_leaf_batch", lb); lib().dm_tune(b"mc_skip_horizon", sk)
+        pm = None if 'M' not in name else R.sample_order(200, 128).to(dev)
         def run():
             return R.shade_mc(f, fj, g["pts"], g["nrm"], g["vd"], rd, rs, mat.mc_cfg, ren.ray_tracer, mat.light[0], mat.tab_d,
                               mat.tab_s, want_aux=False, perm=pm)[0]
@@ -28,4 +33,4 @@ for vid in (3, 40):
         for _ in range(5): col = run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(f"view {vid} pn={n} {name:16s}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  checksum {float(col.sum()):.4f}")
+        print(f"view {vid} pn={n} {name:30s} perm={'morton' if pm is not None else 'id'}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  checksum {float(col.sum()):.4f}")
