@@ -107,7 +107,7 @@ struct McParams {
     float *color, *jac, *reg_sums;
     float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
     uint32_t* hit_bits;
-    int refill_below, leaf_batch, skip_horizon;   // traversal scheduling knobs (dm_tune)
+    int skip_horizon;   // dm_tune knob
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
@@ -173,145 +173,88 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
         float Ud[3] = {0, 0, 0}, Vd[3] = {0, 0, 0};    // d/da of the above with fh held fixed
         float Wd[3] = {0, 0, 0};                       // sum L*w*dfh/da
 
-        // ---- sample loop.  Lanes own the sample slots lane, lane+32, ... (in `perm` order).  BVH traversal is the
-        // cost and its length varies wildly per ray, so lanes do NOT advance in lock-step: each lane runs a small
-        // state machine (set up a ray -> traverse step by step -> finalise), and the warp only leaves the
-        // traversal loop to finalise / refill when fewer than REFILL_BELOW lanes still have a ray in flight
-        // (Aila-Laine style persistent rays; keeps SIMT efficiency high in both phases).
-        const int REFILL_BELOW = P.refill_below, LEAF_BATCH = P.leaf_batch;
-        int slot = lane;
-        bool have = false, pending = false, hit = false, spec = false;
-        int s_cur = 0;
-        D3 d;
-        d.x = d.y = d.z = mkd(0.f);
-        f3 ro = mk3(0, 0, 0), rinv = mk3(0, 0, 0), roi = mk3(0, 0, 0);
-        int cur = 0, sp = 0;
-        int stack[DM_BVH_STACK];
-        while (true) {
-            if (!have) {
-                if (pending) {
-                    pending = false;
-                    if (P.hit_bits && hit) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s_cur >> 5), 1u << (s_cur & 31));
-                    if (!hit) {
-                        // ---- unoccluded sample: BRDF terms (value and d/da) and the env texel (:490-507, :615-677)
-                        const f3 n = mk3(px.n[0], px.n[1], px.n[2]), v = mk3(px.v[0], px.v[1], px.v[2]);
-                        const Dual aD = mkd(px.a, 1.0f);
-                        D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;   // H = normalize(v + d) (:513-514)
-                        Dual hl = dsqrt(ddot(h, h));
-                        float hlc = fmaxf(hl.v, 1e-12f);
-                        Dual hinv = mkd(1.0f / hlc, (hl.v > 1e-12f) ? (-hl.d / (hlc * hlc)) : 0.0f);
-                        D3 Hh; Hh.x = h.x * hinv; Hh.y = h.y * hinv; Hh.z = h.z * hinv;
-                        Dual HoV = dclamp01(ddot(Hh, v));
-                        Dual fh = dpow5(dclamp01(1.0f - HoV));
-                        Dual NoL = dclamp01(ddot(d, n));
-                        Dual NoH = dclamp01(ddot(Hh, n));
-                        Dual Dg = ggx_D(NoH, aD);
-                        Dual G = mkd(px.g1v, px.g1d) * ggx_G1(NoL, aD);
-                        Dual pdf;
-                        if (!spec) pdf = mkd(NoL.v / PI_F * kd_pdf);
-                        else pdf = Dg * NoH / (4.0f * HoV + 1e-5f) * ks_pdf;
-                        Dual w = Dg * G / (4.0f * px.NoV * pdf + 1e-5f);
-                        float4 L4 = env_fetch(P.env, P.envH, P.envW, mk3(d.x.v, d.y.v, d.z.v));
-                        const float L[3] = {L4.x, L4.y, L4.z};
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            if (!spec) Ld[c] += L[c]; else Ls[c] += L[c];
-                            float lw = L[c] * w.v;
-                            U[c] += lw; V[c] += lw * fh.v;
-                            float lwd = L[c] * w.d;
-                            Ud[c] += lwd; Vd[c] += lwd * fh.v;
-                            Wd[c] += lw * fh.d;
-                        }
-                    }
-                }
-                while (slot < S) {
-                    // ---- next sample of this lane: direction (value and d/da), :554-596
-                    int s = P.perm ? P.perm[slot] : slot;
-                    slot += 32;
-                    s_cur = s;
-                    spec = s >= nd;
-                    if (!spec) {
-                        float az = s_td[3 * s] + px.rd;
-                        az = az - floorf(az / TWO_PI_F) * TWO_PI_F;  // % (2 pi)
-                        float sn, cs;
-                        sincosf(az, &sn, &cs);
-                        float cx = s_td[3 * s + 1] * cs, cy = s_td[3 * s + 1] * sn, cz = s_td[3 * s + 2];
-                        d.x = mkd(cx * px.xd[0] + cy * px.yd[0] + cz * px.n[0]);
-                        d.y = mkd(cx * px.xd[1] + cy * px.yd[1] + cz * px.n[1]);
-                        d.z = mkd(cx * px.xd[2] + cy * px.yd[2] + cz * px.n[2]);
-                    } else {
-                        const int j = s - nd;
-                        float ue = s_ts[2 * j + 1];
-                        float phi = s_ts[2 * j] + px.rs;
-                        phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
-                        float sn, cs;
-                        sincosf(phi, &sn, &cs);
-                        const Dual aD = mkd(px.a, 1.0f);
-                        // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
-                        Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
-                        Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
-                        Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
-                        Dual cx = st * cs, cy = st * sn;
-                        d.x = cx * px.xs[0] + cy * px.ys[0] + ct * px.r[0];
-                        d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
-                        d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
-                    }
-                    // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless
-                    // the aux light maps are requested its radiance is never used, so the ray need not be traced
-                    if (P.skip_horizon && spec && !P.spec_light && !P.hit_bits &&
-                        (d.x.v * px.n[0] + d.y.v * px.n[1] + d.z.v * px.n[2]) <= 0.0f) continue;
-                    // occlusion ray from p + 1e-5 d (:493-494)
-                    ro = mk3(px.p[0] + d.x.v * 1e-5f, px.p[1] + d.y.v * 1e-5f, px.p[2] + d.z.v * 1e-5f);
-                    rinv = mk3(1.0f / d.x.v, 1.0f / d.y.v, 1.0f / d.z.v);
-                    roi = mk3(ro.x * rinv.x, ro.y * rinv.y, ro.z * rinv.z);
-                    cur = P.bvh.root; sp = 0;
-                    have = true;
-                    break;
-                }
+        // ---- sample loop: the two sample families are visited in separate warp-aligned segments (lane = sample slot).
+        // Measured alternatives (profiles/r01_shade_experiments.md): persistent per-lane ray state machines with warp refill
+        // and batched leaf tests were 10-60 % SLOWER than this lock-step loop once the per-step cost was cut
+        // (precomputed triangle edges, pre-widened slabs, occlusion before BRDF math).
+        const int it_d = (nd + 31) >> 5, it_s = (ns + 31) >> 5;
+        for (int it = 0; it < it_d + it_s; ++it) {
+            const bool spec = it >= it_d;
+            const int slot = (spec ? (it - it_d) : it) * 32 + lane;
+            if (slot >= (spec ? ns : nd)) continue;
+            int s = spec ? nd + slot : slot;
+            if (P.perm) s = P.perm[s];
+            // ---- sample direction (value and d/da), :554-596
+            D3 d;
+            if (!spec) {
+                float az = s_td[3 * s] + px.rd;
+                az = az - floorf(az / TWO_PI_F) * TWO_PI_F;  // % (2 pi)
+                float sn, cs;
+                sincosf(az, &sn, &cs);
+                float cx = s_td[3 * s + 1] * cs, cy = s_td[3 * s + 1] * sn, cz = s_td[3 * s + 2];
+                d.x = mkd(cx * px.xd[0] + cy * px.yd[0] + cz * px.n[0]);
+                d.y = mkd(cx * px.xd[1] + cy * px.yd[1] + cz * px.n[1]);
+                d.z = mkd(cx * px.xd[2] + cy * px.yd[2] + cz * px.n[2]);
+            } else {
+                const int j = s - nd;
+                float ue = s_ts[2 * j + 1];
+                float phi = s_ts[2 * j] + px.rs;
+                phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
+                float sn, cs;
+                sincosf(phi, &sn, &cs);
+                const Dual aD = mkd(px.a, 1.0f);
+                // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
+                Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
+                Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
+                Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
+                Dual cx = st * cs, cy = st * sn;
+                d.x = cx * px.xs[0] + cy * px.ys[0] + ct * px.r[0];
+                d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
+                d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
             }
-            unsigned busy = __ballot_sync(0xffffffffu, have);
-            if (busy == 0u) break;
-            do {
-                // ---- node phase: every lane whose ray sits on an internal node takes ONE step
-                if (have && cur >= 0) {
-                    const float4* nd4 = P.bvh.nodes + (int64_t)cur * 4;
-                    float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
-                    float tl, tr;
-                    bool hl_ = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rinv, roi, DM_RT_MAX_DIST, tl);
-                    bool hr_ = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rinv, roi, DM_RT_MAX_DIST, tr);
-                    int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-                    if (hl_ && hr_) {
-                        bool lfirst = tl <= tr;
-                        if (sp < DM_BVH_STACK) stack[sp++] = lfirst ? cr : cl;
-                        cur = lfirst ? cl : cr;
-                    } else if (hl_) cur = cl;
-                    else if (hr_) cur = cr;
-                    else if (sp == 0) { have = false; pending = true; hit = false; }
-                    else cur = stack[--sp];
-                }
-                // ---- leaf phase: triangle tests are the expensive, poorly-filled part of a lock-step traversal, so
-                // lanes that reached a leaf wait until enough of them have one (or nobody can advance on nodes)
-                const unsigned at_leaf = __ballot_sync(0xffffffffu, have && cur < 0);
-                const unsigned at_node = __ballot_sync(0xffffffffu, have && cur >= 0);
-                if (at_leaf != 0u && (__popc(at_leaf) >= LEAF_BATCH || at_node == 0u)) {
-                    if (have && cur < 0) {
-                        int code = ~cur;
-                        int first = code >> 2, cnt = (code & 3) + 1;
-                        const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
-                        bool h_ = false;
-                        for (int k = 0; k < cnt; ++k) {
-                            const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
-                            float4 A = __ldg(tp), Bv = __ldg(tp + 1), Cv = __ldg(tp + 2);
-                            float u_, v_;
-                            h_ = h_ || (tri_hit_pre(ro, dv, A, Bv, Cv, u_, v_) < DM_RT_MAX_DIST);
-                        }
-                        if (h_) { have = false; pending = true; hit = true; }
-                        else if (sp == 0) { have = false; pending = true; hit = false; }
-                        else cur = stack[--sp];
-                    }
-                }
-                busy = __ballot_sync(0xffffffffu, have);
-            } while (__popc(busy) >= REFILL_BELOW);
+            const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+            // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless the
+            // aux light maps are requested its radiance is never used, so the ray need not be traced
+            if (P.skip_horizon && spec && !P.spec_light && !P.hit_bits &&
+                (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f) continue;
+            // ---- occlusion first (:490-507): occluded samples contribute nothing, skip their BRDF math
+            bool hit;
+            {
+                f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
+                float bt, bu, bvv; int bid;
+                hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+            }
+            if (P.hit_bits && hit) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
+            if (hit) continue;
+            // ---- unoccluded sample: BRDF terms (value and d/da) and the env texel (:615-677)
+            const f3 n = mk3(px.n[0], px.n[1], px.n[2]), v = mk3(px.v[0], px.v[1], px.v[2]);
+            const Dual aD = mkd(px.a, 1.0f);
+            D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;   // H = normalize(v + d) (:513-514)
+            Dual hl = dsqrt(ddot(h, h));
+            float hlc = fmaxf(hl.v, 1e-12f);
+            Dual hinv = mkd(1.0f / hlc, (hl.v > 1e-12f) ? (-hl.d / (hlc * hlc)) : 0.0f);
+            D3 Hh; Hh.x = h.x * hinv; Hh.y = h.y * hinv; Hh.z = h.z * hinv;
+            Dual HoV = dclamp01(ddot(Hh, v));
+            Dual fh = dpow5(dclamp01(1.0f - HoV));
+            Dual NoL = dclamp01(ddot(d, n));
+            Dual NoH = dclamp01(ddot(Hh, n));
+            Dual Dg = ggx_D(NoH, aD);
+            Dual G = mkd(px.g1v, px.g1d) * ggx_G1(NoL, aD);
+            Dual pdf;
+            if (!spec) pdf = mkd(NoL.v / PI_F * kd_pdf);
+            else pdf = Dg * NoH / (4.0f * HoV + 1e-5f) * ks_pdf;
+            Dual w = Dg * G / (4.0f * px.NoV * pdf + 1e-5f);
+            float4 L4 = env_fetch(P.env, P.envH, P.envW, dv);
+            const float L[3] = {L4.x, L4.y, L4.z};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!spec) Ld[c] += L[c]; else Ls[c] += L[c];
+                float lw = L[c] * w.v;
+                U[c] += lw; V[c] += lw * fh.v;
+                float lwd = L[c] * w.d;
+                Ud[c] += lwd; Vd[c] += lwd * fh.v;
+                Wd[c] += lw * fh.d;
+            }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -559,14 +502,13 @@ __global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, flo
 
 }  // namespace
 
-static int g_mc_refill = 20, g_mc_leaf_batch = 12, g_mc_skip_horizon = 1;
+static int g_mc_skip_horizon = 1;
 
 /* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
 extern "C" int dm_tune(const char* key, int value) {
     if (!key) return DM_EINVAL;
-    if (!strcmp(key, "mc_refill")) g_mc_refill = value;
-    else if (!strcmp(key, "mc_leaf_batch")) g_mc_leaf_batch = value;
-    else if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    else if (!strcmp(key, "mc_refill") || !strcmp(key, "mc_leaf_batch")) { /* retired experiment knobs */ }
     else { dm_set_error("dm_tune: unknown key %s", key); return DM_EINVAL; }
     return DM_OK;
 }
@@ -589,7 +531,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.rand_d = rand_d; P.rand_s = rand_s; P.n = n; P.color = color; P.jac = jac; P.reg_sums = reg_sums;
     P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
-    P.refill_below = g_mc_refill; P.leaf_batch = g_mc_leaf_batch; P.skip_horizon = g_mc_skip_horizon;
+    P.skip_horizon = g_mc_skip_horizon;
     size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float);
     shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();

@@ -1,0 +1,94 @@
+"""CPU tests of the host-side mirrors (a1 batch, schedules, prompt selection, plugin Config surface)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import render as OR
+from oracle import sd as OS
+
+REF = "/root/reference/threestudio_dreammat/threestudio"
+
+
+def test_camera_batch_matches_oracle():
+    from dreammat_b200.scene import DataConfig, FixCameraSet
+    cams = FixCameraSet(DataConfig(width=48, height=48), torch.Generator().manual_seed(0))
+    ids = torch.tensor([0, 17, 63, 127])
+    c = cams.cameras(ids)
+    o = OR.camera_batch(cams.elevation_deg[ids], cams.azimuth_deg[ids], cams.camera_distances[ids], cams.fovy_deg[ids], 48, 48)
+    for k in ("rays_o", "rays_d", "mvp_mtx", "w2c", "c2w", "camera_positions"):
+        assert torch.allclose(c[k], o[k], atol=1e-6), k
+    # configs/dreammat.yaml:11-17 ranges
+    assert float(cams.elevation_deg.min()) >= -20 and float(cams.elevation_deg.max()) <= 45
+    assert float(cams.camera_distances.min()) >= 3 and float(cams.camera_distances.max()) <= 4
+    assert float(cams.fovy_deg.min()) >= 25 and float(cams.fovy_deg.max()) <= 45
+    # stratified azimuths: one per 360/128 degree bin (uncond.py:606-614)
+    bins = torch.floor((cams.azimuth_deg + 180) / (360 / 128)).long()
+    assert torch.equal(bins, torch.arange(128))
+    v, e = cams.collate(torch.Generator().manual_seed(3), 8)
+    assert v.shape == (8,) and int(v.max()) < 128 and int(e.max()) < 5
+
+
+def test_schedules_match_reference_semantics():
+    from dreammat_b200.guidance import C
+    for val, step in (([0, -1.0, -0.5, 2000], 0), ([0, -1.0, -0.5, 2000], 1000), ([0, -1.0, -0.5, 2000], 5000),
+                      ([500, 0.2, 0.02, 501], 500), ([500, 0.2, 0.02, 501], 501), (1.05, 10), ([0, 0.0, -0.5, 2000], 300)):
+        assert C(val, 0, step) == OS.C(val, 0, step)
+    assert C([0, -1.0, -0.5, 2000], 0, 1000) == -0.75
+
+
+def test_prompt_direction_selection():
+    """models/prompt_processors/base.py:281-312: side default, front |az|<45, back |az|>135, overhead el>60 (last wins)."""
+    from dreammat_b200.guidance import PromptProcessorOutput
+    z = torch.zeros(1, 77, 8)
+    pu = PromptProcessorOutput(z, z, z, torch.zeros(4, 77, 8), torch.zeros(4, 77, 8))
+    el = torch.tensor([0.0, 0.0, 0.0, 0.0, 70.0, 0.0])
+    az = torch.tensor([90.0, 10.0, -44.0, 170.0, 10.0, -136.0])
+    assert pu.direction_index(el, az, torch.ones(6)).tolist() == [0, 1, 1, 2, 3, 2]
+    vd = torch.arange(4).float().view(4, 1, 1).expand(4, 77, 8)
+    pu = PromptProcessorOutput(z, z, z + 9, vd, vd + 10)
+    e = pu.get_text_embeddings(el[:2], az[:2], torch.ones(2), True, return_null_text_embeddings=True)
+    assert e.shape == (6, 77, 8) and e[:, 0, 0].tolist() == [0, 1, 10, 11, 9, 9]      # [text | uncond | null]
+
+
+def _ref_fields(path, cls):
+    src = open(path).read()
+    m = re.search(r"class " + cls + r"\b.*?class Config\(.*?\):\n(.*?)\n    cfg: Config", src, re.S)
+    assert m, (path, cls)
+    out = {}
+    for line in m.group(1).splitlines():
+        mm = re.match(r"\s{8}(\w+)\s*:\s*[^=]+=\s*(.+)$", line)
+        if mm:
+            out[mm.group(1)] = mm.group(2).strip()
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree absent (GPU box)")
+def test_plugin_config_surface_matches_reference():
+    """Same Config field names (and scalar defaults) as the reference plugins, so dreammat.yaml parses unchanged."""
+    from dreammat_b200.guidance import StableDiffusionLightGuidance
+    from dreammat_b200.system import DreamMatMaterial
+    for path, cls, mine in ((REF + "/models/guidance/dreammat_guidance.py", "StableDiffusionLightGuidance", StableDiffusionLightGuidance.Config),
+                            (REF + "/models/materials/dreammat_material.py", "DreamMatMaterial", DreamMatMaterial.Config)):
+        ref = _ref_fields(path, cls)
+        assert len(ref) >= 10
+        inst = mine()
+        for name, default in ref.items():
+            assert hasattr(inst, name), f"{cls}.Config lacks field {name}"
+            if re.fullmatch(r"-?[\d.]+|True|False|None|\"[^\"]*\"|'[^']*'", default):
+                assert getattr(inst, name) == eval(default), (cls, name, default, getattr(inst, name))
+
+
+def test_procedural_mesh_and_normalisation():
+    from dreammat_b200.scene import normalize_mesh, procedural_mesh, vertex_normals
+    import numpy as np
+    v, f = procedural_mesh(5000, 0.8, 0)
+    assert 4000 < f.shape[0] < 30000 and abs(float(v.abs().max()) - 0.8) < 1e-6
+    vn = vertex_normals(v, f)
+    assert torch.allclose(vn.norm(dim=-1), torch.ones(v.shape[0]), atol=1e-5)
+    assert float((vn * torch.nn.functional.normalize(v, dim=-1)).sum(-1).mean()) > 0.8      # outward facing
+    # dreammat_mesh.py:163-197: centred, scaled to max |coord| = scale, +y up / +z front -> z up / x front
+    pts = np.array([[0.0, 2.0, 0.0], [0.0, 0.0, 1.0], [0.0, -2.0, -1.0]])
+    out = normalize_mesh(pts, 0.5, "+y", "+z")
+    assert abs(np.abs(out).max() - 0.5) < 1e-12 and out[0, 2] > 0 and abs(out[0, 0]) < 1e-12
