@@ -306,6 +306,7 @@ class DreamMat:
         out = {ev[i][0] + "_ms": ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
         out["dense_ms"] = out.get("vae_fwd_ms", 0) + out.get("unet_cn_ms", 0) + out.get("vae_bwd_ms", 0) + out.get("dense_graphs_ms", 0)
         out["total_ms"] = ev[0][1].elapsed_time(ev[-1][1])
+        out["pn_local"] = getattr(self, "_last_pn", 0)
         return out
 
     def profile_step(self, make_batch, V):
@@ -343,6 +344,7 @@ class DreamMat:
         gbs = [ren.gbuffer(batch["rays_o"][b:b + 1], batch["rays_d"][b:b + 1], batch["mvp_mtx"][b:b + 1],
                            batch["w2c"][b:b + 1], int(batch["view_id"][b])) for b in range(B)]
         total_pn = total_pn_global or sum(g["pn"] for g in gbs)
+        self._last_pn = sum(g["pn"] for g in gbs)
         g_ = getattr(guid, "graphs", None)
         canvas = g_.rgb.view(B, H * W, 3) if (g_ is not None and g_.B == B and rng is None) else torch.empty(B, H * W, 3, device=dev)
         raw = torch.empty(B, H * W, 3, device=dev)            # canvas before the antialias blend
