@@ -57,30 +57,6 @@ __device__ __forceinline__ bool slab2(float lox, float loy, float loz, float hix
     return t0 <= t1;
 }
 
-__device__ __forceinline__ float tri_hit_dev(f3 o, f3 d, f3 a, f3 b, f3 c, float& u, float& v) {
-    f3 e1 = b - a, e2 = c - a, r = o - a;
-    f3 n = cross3(e1, e2);
-    f3 q = cross3(r, d);
-    float inv = 1.0f / dot3(d, n);
-    u = inv * -dot3(q, e2);
-    v = inv * dot3(q, e1);
-    float t = inv * -dot3(n, r);
-    if (!(u >= 0.0f) || u > 1.0f || !(v >= 0.0f) || (u + v) > 1.0f || !(t >= 0.0f)) return 3.0e38f;
-    return t;
-}
-
-__device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 inv,
-                                     float tmax, float& tn) {
-    float ax = (lox - 1e-6f - o.x) * inv.x, bx = (hix + 1e-6f - o.x) * inv.x;
-    float ay = (loy - 1e-6f - o.y) * inv.y, by = (hiy + 1e-6f - o.y) * inv.y;
-    float az = (loz - 1e-6f - o.z) * inv.z, bz = (hiz + 1e-6f - o.z) * inv.z;
-    // fminf/fmaxf drop NaNs (0*inf when the ray lies in a slab plane)
-    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
-    tn = t0;
-    return t0 <= t1;
-}
-
 // ANY=true : returns as soon as some triangle is hit with t < tmax (occlusion rays)
 // ANY=false: closest hit; ties go to the lowest original triangle id (matches the oracle's scan order)
 template <bool ANY>
