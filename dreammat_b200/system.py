@@ -105,10 +105,31 @@ class DreamMatMesh:
 
     __call__ = forward
 
-    def state_dict(self):
-        """Keys / shapes of the reference checkpoint."""
-        return {"encoding.encoding.encoding.params": self.grid, "feature_network.layers.0.weight": self.W1,
-                "feature_network.layers.2.weight": self.W2}
+    # ---- checkpoint compatibility: same keys, shapes and tcnn parameter order as the
+    # reference's `geometry.*` entries, so a Lightning .ckpt written by either side loads into the other
+    def state_dict(self, prefix: str = ""):
+        return {prefix + "encoding.encoding.encoding.params": self.grid, prefix + "feature_network.layers.0.weight": self.W1,
+                prefix + "feature_network.layers.2.weight": self.W2}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "", strict: bool = False):
+        """Accepts the reference's keys (optionally with the `geometry.` prefix of the system checkpoint).  The dead
+        predictors / mesh buffers of the reference checkpoint (dreammat_mesh.py:136-139,207-222) are ignored unless
+        strict."""
+        want = self.state_dict(prefix)
+        used = set()
+        for k, dst in want.items():
+            src = sd.get(k, sd.get("geometry." + k))
+            if src is None:
+                raise KeyError(f"missing key {k} in checkpoint")
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError(f"{k}: shape {tuple(src.shape)} in checkpoint, expected {tuple(dst.shape)}")
+            dst.copy_(src.to(dst.device, torch.float32))
+            used.add(k)
+        if strict:
+            extra = [k for k in sd if k not in used and k.replace("geometry.", "", 1) not in used]
+            if extra:
+                raise KeyError(f"unexpected keys: {extra[:5]}")
+        return self
 
 
 class DreamMatMaterial:

@@ -92,3 +92,20 @@ def test_procedural_mesh_and_normalisation():
     pts = np.array([[0.0, 2.0, 0.0], [0.0, 0.0, 1.0], [0.0, -2.0, -1.0]])
     out = normalize_mesh(pts, 0.5, "+y", "+z")
     assert abs(np.abs(out).max() - 0.5) < 1e-12 and out[0, 2] > 0 and abs(out[0, 0]) < 1e-12
+
+
+def test_geometry_checkpoint_keys_and_layout():
+    """N2: `geometry.encoding.encoding.encoding.params` is tcnn's flat fp32 [12 599 920]; MLP weights [64,32] / [5,64]."""
+    from dreammat_b200.scene import procedural_mesh
+    from dreammat_b200.system import DreamMatMesh
+    geo = DreamMatMesh({"shape_init": "p"}, "cpu", mesh=procedural_mesh(200, 0.8, 0))
+    sd = geo.state_dict("geometry.")
+    assert sd["geometry.encoding.encoding.encoding.params"].shape == (12599920,)
+    assert sd["geometry.feature_network.layers.0.weight"].shape == (64, 32)
+    assert sd["geometry.feature_network.layers.2.weight"].shape == (5, 64)
+    ck = {k: torch.full_like(v, 0.5) for k, v in sd.items()}
+    ck["geometry.albedo_predictor.0.weight_v"] = torch.zeros(3)      # dead reference parameter: ignored
+    geo.load_state_dict(ck)
+    assert float(geo.params.min()) == 0.5 == float(geo.params.max())  # the views alias the one flat buffer
+    with pytest.raises(ValueError):
+        geo.load_state_dict({k: v[:-1] if v.dim() == 1 else v for k, v in ck.items()})
