@@ -65,6 +65,7 @@ SIGNATURES = {
     "dm_gather_canvas_grad": (C.c_int, [P, P, I64, C.c_int, P, P]),
     "dm_antialias_fwd": (C.c_int, [P, P, P, P, I64, I64, C.c_int, P, P]),
     "dm_antialias_bwd": (C.c_int, [P, P, P, P, I64, I64, C.c_int, P, P]),
+    "dm_resize_bilinear": (C.c_int, [P] + [C.c_int] * 6 + [P, C.c_int, P]),
     "dm_adam_step": (C.c_int, [P, P, P, P, I64, F, F, F, F, I32, F, P]),
     "dm_sds_grad": (C.c_int, [P, P, P, C.c_int, I64, F, F, F, F, P, P, P, P]),
     "dm_gemm": (C.c_int, [C.c_int, P, I64, I64, P, I64, I64, P, I64, I64, C.c_int, C.c_int, C.c_int, C.c_int, P,

@@ -5,6 +5,8 @@
 #include <cmath>
 #include "bvh.cuh"
 
+int g_bvh_leaf_max = 4;   // triangles per leaf (dm_tune "bvh_leaf"), 1..4
+
 namespace {
 
 struct Box {
@@ -30,7 +32,7 @@ struct Builder {
         box.init();
         Box cb; cb.init();
         for (int32_t i = first; i < first + count; ++i) { box.grow(tb[perm[i]]); cb.grow(&cent[3 * (size_t)perm[i]]); }
-        if (count <= 4) {
+        if (count <= g_bvh_leaf_max) {
             int32_t lf = (int32_t)leaf_order.size();
             for (int32_t i = first; i < first + count; ++i) leaf_order.push_back(perm[i]);
             return ~((lf << 2) | (count - 1));

@@ -70,8 +70,12 @@ __device__ __forceinline__ bool bvh_trace(const BvhView& bv, f3 o, f3 d, float& 
     best_t = DM_RT_MAX_DIST;
     best_id = -1;
     bu = bvv = 0.0f;
-    while (true) {
-        if (cur >= 0) {
+    bool alive = true;
+    // "while-while" traversal: every lane first descends through internal nodes until it holds a leaf (or has
+    // nothing left); the warp reconverges there, so the expensive triangle tests run with all leaf-holding lanes
+    // active instead of the ~7/32 an interleaved node/leaf loop gives (profiles/r01_launches_summary.md).
+    while (alive) {
+        while (alive && cur >= 0) {
             const float4* n = bv.nodes + (int64_t)cur * 4;
             float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
             float tl, tr;
@@ -79,20 +83,16 @@ __device__ __forceinline__ bool bvh_trace(const BvhView& bv, f3 o, f3 d, float& 
             bool hr = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, inv, oi, best_t, tr);
             int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
             if (hl && hr) {
-                // near child first
-                bool lfirst = tl <= tr;
-                int nearc = lfirst ? cl : cr, farc = lfirst ? cr : cl;
-                if (sp < DM_BVH_STACK) stack[sp++] = farc;
-                cur = nearc;
-                continue;
-            } else if (hl) {
-                cur = cl;
-                continue;
-            } else if (hr) {
-                cur = cr;
-                continue;
-            }
-        } else {
+                bool lfirst = tl <= tr;      // near child first
+                if (sp < DM_BVH_STACK) stack[sp++] = lfirst ? cr : cl;
+                cur = lfirst ? cl : cr;
+            } else if (hl) cur = cl;
+            else if (hr) cur = cr;
+            else if (sp == 0) alive = false;
+            else cur = stack[--sp];
+        }
+        if (!alive) break;
+        {
             int code = ~cur;
             int first = code >> 2, cnt = (code & 3) + 1;
             for (int k = 0; k < cnt; ++k) {
@@ -100,10 +100,10 @@ __device__ __forceinline__ bool bvh_trace(const BvhView& bv, f3 o, f3 d, float& 
                 float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
                 float u, v;
                 float t = tri_hit_pre(o, d, A, B, C, u, v);
-                int id = ANY ? 0 : __ldg(bv.ids + first + k);
                 if (ANY) {
-                    if (t < best_t) { best_t = t; best_id = id; return true; }
+                    if (t < best_t) { best_t = t; best_id = 0; return true; }
                 } else {
+                    int id = __ldg(bv.ids + first + k);
                     if (t < best_t || (t == best_t && best_id >= 0 && id < best_id)) {
                         best_t = t; best_id = id; bu = u; bvv = v;
                     }

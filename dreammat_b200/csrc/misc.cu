@@ -150,6 +150,35 @@ __global__ void aa_bwd_kernel(const float* __restrict__ dout, const int32_t* __r
     atomicAdd(din + d * c + ch, -g);
 }
 
+// F.interpolate(mode="bilinear", align_corners=False) on NHWC fp32 (dreammat_guidance.py:507-513) and its adjoint
+__device__ __forceinline__ void bil_src(int dst, float scale, int in_size, int& i0, int& i1, float& l) {
+    float src = ((float)dst + 0.5f) * scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src; if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l = src - (float)i0;
+}
+__global__ void resize_bilinear_kernel(const float* __restrict__ in, int n, int Hi, int Wi, int Ho, int Wo, int c,
+                                       float* __restrict__ out, int adjoint) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t tot = (int64_t)n * Ho * Wo * c;
+    if (i >= tot) return;
+    int ch = (int)(i % c); int64_t r = i / c; int xo = (int)(r % Wo); r /= Wo; int yo = (int)(r % Ho); int b = (int)(r / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bil_src(yo, (float)Hi / (float)Ho, Hi, y0, y1, ly);
+    bil_src(xo, (float)Wi / (float)Wo, Wi, x0, x1, lx);
+    const int64_t base = (int64_t)b * Hi * Wi;
+    const int64_t a00 = ((base + (int64_t)y0 * Wi + x0) * c + ch), a01 = ((base + (int64_t)y0 * Wi + x1) * c + ch);
+    const int64_t a10 = ((base + (int64_t)y1 * Wi + x0) * c + ch), a11 = ((base + (int64_t)y1 * Wi + x1) * c + ch);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    if (!adjoint) {
+        out[i] = w00 * in[a00] + w01 * in[a01] + w10 * in[a10] + w11 * in[a11];
+    } else {   // `in` is d(out) [n,Ho,Wo,c]; `out` is d(in) [n,Hi,Wi,c], pre-zeroed
+        float g = in[i];
+        atomicAdd(out + a00, w00 * g); atomicAdd(out + a01, w01 * g); atomicAdd(out + a10, w10 * g); atomicAdd(out + a11, w11 * g);
+    }
+}
+
 // CSD combine (dreammat_guidance.py:475-481, 584-594) with the 10 diagnostic sums.
 __global__ void __launch_bounds__(256) sds_kernel(const float* __restrict__ e, const float* __restrict__ noise,
                                                   const float* __restrict__ w, int B, int64_t chw, float ct, float cu,
@@ -260,6 +289,17 @@ extern "C" int dm_antialias_bwd(const float* dout, const int32_t* dst, const int
     if (k == 0) return DM_OK;
     DM_REQUIRE(dst && src && alpha, "null pointer");
     aa_bwd_kernel<<<(unsigned)dm_ceil_div(k * c, 256), 256, 0, st>>>(dout, dst, src, alpha, k, c, din);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_resize_bilinear(const float* in, int n, int Hi, int Wi, int Ho, int Wo, int c, float* out, int adjoint,
+                                  void* stream) {
+    DM_REQUIRE(in && out && n > 0 && c > 0, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adjoint) DM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * Hi * Wi * c, st));
+    int64_t tot = (int64_t)n * Ho * Wo * c;
+    resize_bilinear_kernel<<<(unsigned)dm_ceil_div(tot, 256), 256, 0, st>>>(in, n, Hi, Wi, Ho, Wo, c, out, adjoint);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

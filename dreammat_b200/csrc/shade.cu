@@ -503,11 +503,13 @@ __global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, flo
 }  // namespace
 
 static int g_mc_skip_horizon = 1;
+extern int g_bvh_leaf_max;
 
 /* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
 extern "C" int dm_tune(const char* key, int value) {
     if (!key) return DM_EINVAL;
     if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    else if (!strcmp(key, "bvh_leaf")) g_bvh_leaf_max = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(key, "mc_refill") || !strcmp(key, "mc_leaf_batch")) { /* retired experiment knobs */ }
     else { dm_set_error("dm_tune: unknown key %s", key); return DM_EINVAL; }
     return DM_OK;

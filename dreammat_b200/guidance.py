@@ -347,9 +347,8 @@ class StableDiffusionLightGuidance:
             latents = rgb.permute(0, 3, 1, 2).contiguous()
         else:
             if rgb.shape[1] != 512 or rgb.shape[2] != 512:
-                # :507-513 bilinear resize to 512^2 before the VAE (host op; 512^2 renders skip it)
-                rgb = torch.nn.functional.interpolate(rgb.permute(0, 3, 1, 2), (512, 512), mode="bilinear",
-                                                      align_corners=False).permute(0, 2, 3, 1)
+                # :507-513 bilinear resize to 512^2 before the VAE (512^2 renders skip it)
+                rgb = R.resize_bilinear(rgb, 512, 512)
             latents = self.encode_images(rgb, kwargs.get("vae_eps"))
         cond = kwargs.get("condition_map")
         ctx3 = prompt_utils.get_text_embeddings(elevation, azimuth, camera_distances, self.cfg.view_dependent_prompting,

@@ -353,3 +353,28 @@ def sds_grad(eps_pred, noise, w, c_text, c_uncond, c_null, c_noise):
     check(lib().dm_sds_grad(ptr(eps_pred), ptr(noise), ptr(w), B, chw, c_text, c_uncond, c_null, c_noise, ptr(grad),
                             ptr(dlat), ptr(sums), stream_ptr()), "dm_sds_grad")
     return grad, dlat, sums
+
+
+class _ResizeBilinear(torch.autograd.Function):
+    """F.interpolate(x, (Ho, Wo), mode='bilinear', align_corners=False) on NHWC fp32 (dreammat_guidance.py:507-513)."""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        x = _f32c(x)
+        n, Hi, Wi, c = x.shape
+        out = torch.empty(n, Ho, Wo, c, device=x.device)
+        check(lib().dm_resize_bilinear(ptr(x), n, Hi, Wi, Ho, Wo, c, ptr(out), 0, stream_ptr()), "dm_resize_bilinear")
+        ctx.shape = (n, Hi, Wi, Ho, Wo, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, Hi, Wi, Ho, Wo, c = ctx.shape
+        dout = _f32c(dout)
+        din = torch.empty(n, Hi, Wi, c, device=dout.device)
+        check(lib().dm_resize_bilinear(ptr(dout), n, Hi, Wi, Ho, Wo, c, ptr(din), 1, stream_ptr()), "dm_resize_bilinear")
+        return din, None, None
+
+
+def resize_bilinear(x_bhwc, Ho, Wo):
+    return _ResizeBilinear.apply(x_bhwc, Ho, Wo)

@@ -302,6 +302,8 @@ class DreamMat:
         self.v = torch.zeros_like(geometry.params)
         self.global_step = 0
         self.world_size, self.rank = 1, 0
+        # dreammat_guidance.py:507-513: renders that are not 512x512 are resized (bilinear) to 512x512 before the VAE
+        self.resize_to_vae = True
 
     def C(self, v):
         from .guidance import C
@@ -367,7 +369,9 @@ class DreamMat:
         total_pn = total_pn_global or sum(g["pn"] for g in gbs)
         self._last_pn = sum(g["pn"] for g in gbs)
         g_ = getattr(guid, "graphs", None)
-        canvas = g_.rgb.view(B, H * W, 3) if (g_ is not None and g_.B == B and rng is None) else torch.empty(B, H * W, 3, device=dev)
+        resize = self.resize_to_vae and (H != 512 or W != 512)
+        use_graphs = g_ is not None and g_.B == B and rng is None
+        canvas = g_.rgb.view(B, H * W, 3) if (use_graphs and not resize) else torch.empty(B, H * W, 3, device=dev)
         raw = torch.empty(B, H * W, 3, device=dev)            # canvas before the antialias blend
         check(lib().dm_fill(ptr(raw), raw.numel(), 1.0, st), "dm_fill")
         reg_sums = torch.zeros(2, device=dev)
@@ -395,8 +399,11 @@ class DreamMat:
             check(lib().dm_antialias_fwd(ptr(raw[b]), ptr(aa[0]) if k_aa else None, ptr(aa[1]) if k_aa else None,
                                          ptr(aa[2]) if k_aa else None, k_aa, H * W, 3, ptr(canvas[b]), st), "dm_antialias_fwd")
             saved.append((g, pj, f, fj, jac))
-        use_graphs = getattr(guid, "graphs", None) is not None and guid.graphs.B == B and rng is None
         comp_rgb = canvas.view(B, H, W, 3)
+        vae_in = comp_rgb
+        if resize:
+            vae_in = g_.rgb if use_graphs else torch.empty(B, 512, 512, 3, device=dev)
+            check(lib().dm_resize_bilinear(ptr(comp_rgb), B, H, W, 512, 512, 3, ptr(vae_in), 0, st), "dm_resize_bilinear")
         self._mark("render_fwd")
         ctx3 = self.prompt_utils.get_text_embeddings(batch["elevation"], batch["azimuth"], batch["camera_distances"],
                                                      guid.cfg.view_dependent_prompting, return_null_text_embeddings=True)
@@ -404,12 +411,12 @@ class DreamMat:
             # dense section replayed from three captured CUDA graphs (VAE fwd | ControlNet+UNet | VAE bwd)
             drgb, sums = guid.graph_step(batch["condition_map"], ctx3, lam_sds * B / Bg, mark=self._mark)
             loss_sds = sums[0] / Bg
-            dcanvas = drgb.view(B, H * W, 3)
+            dvae = drgb
         else:
             # guidance (dreammat_guidance.py:536-602): VAE encode with grad, ControlNet + UNet x3 under no_grad, CSD gradient
             from .guidance import _SDSLoss
-            comp_rgb.requires_grad_(True)
-            lat = guid.encode_images(comp_rgb, rng["vae_eps"].to(dev) if rng is not None else None)
+            vae_in = vae_in.detach().requires_grad_(True)
+            lat = guid.encode_images(vae_in, rng["vae_eps"].to(dev) if rng is not None else None)
             self._mark("vae_fwd")
             grad, dlat, sums = guid.compute_grad_sds(lat, batch["condition_map"], ctx3, rng["t"].to(dev) if rng is not None else None,
                                                      rng["noise"].to(dev) if rng is not None else None)
@@ -417,7 +424,12 @@ class DreamMat:
             loss_sds = _SDSLoss.apply(lat, dlat, sums[0] / B) * (B / Bg)          # mean over the GLOBAL batch of views
             (lam_sds * loss_sds).backward()
             self._mark("vae_bwd")
-            dcanvas = comp_rgb.grad.view(B, H * W, 3)
+            dvae = vae_in.grad
+        if resize:
+            dcanvas = torch.empty(B, H * W, 3, device=dev)
+            check(lib().dm_resize_bilinear(ptr(dvae.contiguous()), B, H, W, 512, 512, 3, ptr(dcanvas), 1, st), "dm_resize_bilinear")
+        else:
+            dcanvas = dvae.reshape(B, H * W, 3)
         gout = {"grad_norm": sums[1].sqrt()}
         # backward into the hash grid / MLP
         geo.grads.zero_()

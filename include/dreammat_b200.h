@@ -155,6 +155,12 @@ int dm_antialias_fwd(const float* in, const int32_t* dst, const int32_t* src, co
 int dm_antialias_bwd(const float* dout, const int32_t* dst, const int32_t* src, const float* alpha, int64_t k,
                      int64_t n_pix, int c, float* din, void* stream);
 
+/* F.interpolate(rgb, (512,512), mode="bilinear", align_corners=False) before the VAE when the render is not 512^2
+ * (dreammat_guidance.py:507-513), NHWC fp32.  adjoint=0: in [n,Hi,Wi,c] -> out [n,Ho,Wo,c]; adjoint=1: in is
+ * d out [n,Ho,Wo,c] and out receives d in [n,Hi,Wi,c]. */
+int dm_resize_bilinear(const float* in, int n, int Hi, int Wi, int Ho, int Wo, int c, float* out, int adjoint,
+                       void* stream);
+
 /* ------------------------------------------------------------------ optimiser (a9)
  * torch.optim.Adam as configured by systems/utils.py:34-53 + configs/dreammat.yaml:110-115 */
 int dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -18,13 +18,12 @@ for vid in (3,):
     f = torch.randn(n, 5, device=dev); fj = torch.randn(n, 5, device=dev)
     rd, rs = torch.rand(n, device=dev), torch.rand(n, device=dev)
     from dreammat_b200._cabi import lib
-    variants = [(f"refill{r} leaf{l}", r, l, 1) for (r, l) in ((1, 1), (1, 8), (2, 4), (4, 1), (4, 8), (6, 8), (8, 1), (8, 4), (8, 8),
-                                                                    (8, 16), (12, 8), (12, 1))] + [("M refill4 leaf8", 4, 8, 1), ("M refill1 leaf1", 1, 1, 1), ("M refill8 leaf8", 8, 8, 1)]
-    for name, rf, lb, sk in variants:
-        lib().dm_tune(b"mc_refill", rf); lib().dm_tune(b"mc_leaf_batch", lb); lib().dm_tune(b"mc_skip_horizon", sk)
-        pm = None if 'M' not in name else R.sample_order(200, 128).to(dev)
+    for name, leaf in (("leaf<=4", 4), ("leaf<=2", 2), ("leaf<=1", 1), ("leaf<=3", 3)):
+        lib().dm_tune(b"bvh_leaf", leaf)
+        bvh = R.Bvh(mesh[0], mesh[1])
+        pm = None
         def run():
-            return R.shade_mc(f, fj, g["pts"], g["nrm"], g["vd"], rd, rs, mat.mc_cfg, ren.ray_tracer, mat.light[0], mat.tab_d,
+            return R.shade_mc(f, fj, g["pts"], g["nrm"], g["vd"], rd, rs, mat.mc_cfg, bvh, mat.light[0], mat.tab_d,
                               mat.tab_s, want_aux=False, perm=pm)[0]
         for _ in range(2): col = run()
         torch.cuda.synchronize()

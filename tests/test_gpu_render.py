@@ -256,3 +256,18 @@ def test_sds_combine_matches_formula(ops):
     assert rel_err(dlat.cpu(), ref / B) < 1e-6
     assert abs(float(sums[1]) ** 0.5 - float(ref.norm())) < 1e-3
     assert abs(float(sums[7]) ** 0.5 - float(noise.norm())) < 1e-3
+
+
+def test_resize_bilinear_matches_torch(ops):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    for (Hi, Wi, Ho, Wo) in ((64, 64, 32, 32), (24, 40, 32, 32), (32, 32, 32, 32), (100, 60, 37, 41)):
+        x = torch.rand(2, Hi, Wi, 3, generator=g)
+        xc = cu(x).requires_grad_(True)
+        y = ops.resize_bilinear(xc, Ho, Wo)
+        xr = x.clone().requires_grad_(True)
+        ref = F.interpolate(xr.permute(0, 3, 1, 2), (Ho, Wo), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        assert rel_err(y.detach().cpu(), ref.detach()) < 1e-6
+        dy = torch.rand(ref.shape, generator=g)
+        ref.backward(dy); y.backward(cu(dy))
+        assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
