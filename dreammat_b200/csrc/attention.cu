@@ -16,7 +16,7 @@
 //                          P_j -> fp16 into the 128B-swizzled K-major tile, O accumulated in registers
 //                          (O_j is read back from TMEM one block late, so the tensor pipe never waits
 //                          for the rescale).
-// Two CTAs are resident per SM (<= 96 KB smem, 128 TMEM columns each): while one CTA's softmax
+// Two CTAs are resident per SM (<= 96 KB smem, 256 TMEM columns each; S is double-buffered in TMEM): while one CTA's softmax
 // warps work through their exponentials (the MUFU unit, not the tensor pipe, bounds head_dim 64
 // attention), the other CTA's MMAs run.
 #include <cuda.h>
@@ -35,7 +35,7 @@ constexpr int Q_BYTES = AQ * HD * 2;     // 16 KB
 constexpr int KV_BYTES = AK * HD * 2;    // 8 KB
 constexpr int P_BYTES = AQ * AK * 2;     // 16 KB
 constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + P_BYTES + 1024 + 256;
-constexpr int ATT_TMEM_COLS = 128;       // S: cols [0,64), O_j: cols [64,128)
+constexpr int ATT_TMEM_COLS = 256;       // S double buffer: cols [0,64) and [64,128); O_j: cols [128,192)
 
 struct AttnParams {
     int Nq, Nk, heads;
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     const uint32_t q_full = bars;
     auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
     auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
-    const uint32_t s_full = bars + 8u * (1 + 2 * KV_STAGES), p_full = s_full + 8u, o_full = p_full + 8u;
+    const uint32_t s_full0 = bars + 8u * (1 + 2 * KV_STAGES), p_full = s_full0 + 16u, o_full = p_full + 8u;
+    auto s_full = [&](int jj) { return s_full0 + 8u * (uint32_t)(jj & 1); };
     const uint32_t tmem_slot = o_full + 8u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
         mbar_init(q_full, 1);
         for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+        mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ld_shared_u32(tmem_slot);
-    const uint32_t tmem_S = tmem, tmem_O = tmem + 64;
+    const uint32_t tmem_O = tmem + 128;
+    auto tmem_S = [&](int jj) { return tmem + 64u * (uint32_t)(jj & 1); };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -123,14 +125,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
             constexpr uint32_t IDESC_O = (1u << 4) | (FMT << 7) | (FMT << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
             const uint64_t dQ = make_sw128_desc(sQ), dP = make_sw128_desc(sP);
             mbar_wait(q_full, 0);
-            int stage = 0; uint32_t phase = 0;
+            int stage = 0; uint32_t phase = 0;       // stage / phase of block j (V_j, and K_j already consumed)
+            int kstage = 0; uint32_t kphase = 0;     // stage / phase of the next K block to turn into S
             // S(0)
             mbar_wait(kv_full(0), 0);
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_S, dQ + 2 * k, make_sw128_desc(sK) + 2 * k, IDESC_S, k != 0);
-            umma_commit(s_full);
+            for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_S(0), dQ + 2 * k, make_sw128_desc(sK) + 2 * k, IDESC_S, k != 0);
+            umma_commit(s_full(0));
+            if (++kstage == KV_STAGES) { kstage = 0; kphase ^= 1u; }
             for (int j = 0; j < nkb; ++j) {
+                // S(j+1) goes into the other S buffer right away, so the softmax warps never wait for the tensor pipe.
+                // That buffer held S(j-1), which the softmax warps finished reading before they published P(j-1).
+                if (j + 1 < nkb) {
+                    mbar_wait(kv_full(kstage), kphase);
+                    tc_fence_after();
+                    const uint64_t dK = make_sw128_desc(sK + kstage * KV_BYTES);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_S(j + 1), dQ + 2 * k, dK + 2 * k, IDESC_S, k != 0);
+                    umma_commit(s_full(j + 1));
+                    if (++kstage == KV_STAGES) { kstage = 0; kphase ^= 1u; }
+                }
                 // O_j = P_j V_j once the softmax warps have published P_j
                 mbar_wait(p_full, (uint32_t)(j & 1));
                 tc_fence_after();
@@ -140,14 +155,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
                 umma_commit(o_full);
                 umma_commit(kv_empty(stage));
                 if (++stage == KV_STAGES) { stage = 0; phase ^= 1u; }
-                if (j + 1 < nkb) {
-                    mbar_wait(kv_full(stage), phase);
-                    tc_fence_after();
-                    const uint64_t dK = make_sw128_desc(sK + stage * KV_BYTES);
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_S, dQ + 2 * k, dK + 2 * k, IDESC_S, k != 0);
-                    umma_commit(s_full);
-                }
             }
         }
     } else {
@@ -160,13 +167,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
         float m_run = -INFINITY, l_run = 0.f;
         const uint32_t p_row = sP + (uint32_t)row * 128u;
         for (int j = 0; j < nkb; ++j) {
-            mbar_wait(s_full, (uint32_t)(j & 1));
+            mbar_wait(s_full(j), (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             uint32_t sv[64];
             {
                 uint32_t t0[32], t1[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_addr, t0);
-                tmem_ld_32x32b_x32(tmem_S + lane_addr + 32, t1);
+                tmem_ld_32x32b_x32(tmem_S(j) + lane_addr, t0);
+                tmem_ld_32x32b_x32(tmem_S(j) + lane_addr + 32, t1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) { sv[c] = t0[c]; sv[32 + c] = t1[c]; }
