@@ -237,7 +237,7 @@ def run_ours(args):
         out["unet_controlnet_ms_per_step"] = sec.get("unet_cn_ms")
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -339,7 +339,19 @@ def run_reference(args):
            "data": "synthetic", "config": {"workload": "north-star: %dx%d, %d-view batch" % (args.res, args.res, args.views)},
            "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": "port", "sample": SAMPLE_DESC},
            "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_RESULT_FD = None
+
+
+def emit(obj):
+    line = json.dumps(obj) + "\n"
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        sys.stdout.write(line); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line.encode())
 
 
 def main():
@@ -357,6 +369,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner, nvcc/ninja chatter)
+    # are sent to stderr for the whole run and the result line is written to the saved descriptor.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

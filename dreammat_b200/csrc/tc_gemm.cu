@@ -47,7 +47,7 @@ struct GemmParams {
     const void* residual; int ld_res; int64_t res_batch_stride;
     float alpha;                            // applied to the accumulator first
     float out_scale;                        // applied last
-    int act;                                // 0 none, 1 silu, 2 gelu(erf)
+    int act;                                // 0 none, 1 silu, 2 gelu(erf), 3 geglu (interleaved value|gate)
 };
 
 template <typename T> struct Cvt;
@@ -189,6 +189,41 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
             char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
             const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+            if (p.act == 3) {
+                // GEGLU epilogue: the weight rows come interleaved as [32 value | 32 gate] blocks (host side,
+                // dense_ops.geglu_interleave), so every 64 accumulator columns give 32 outputs value * gelu(gate)
+                // and the [M, N] projection never goes to HBM.  Output row length is N / 2.
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    uint32_t v[32], g[32];
+                    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+                    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c0 + 32), g);
+                    tmem_ld_wait();
+                    if (c0 + 64 >= BN) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                    }
+                    const int n0 = n_tile * BN + c0;
+                    if (!row_ok || n0 >= p.N) continue;
+                    T* o = reinterpret_cast<T*>(outp) + (n0 >> 1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        T* h = reinterpret_cast<T*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = q * 8 + j;
+                            float a = __uint_as_float(v[c]) * p.alpha, b = __uint_as_float(g[c]) * p.alpha;
+                            if (bias) { a += Cvt<T>::to_f(bias[n0 + c]); b += Cvt<T>::to_f(bias[n0 + 32 + c]); }
+                            h[j] = Cvt<T>::from_f(a * (0.5f * b * (1.0f + erff(b * 0.70710678118654752f))) * p.out_scale);
+                        }
+                        reinterpret_cast<uint4*>(o)[q] = u;
+                    }
+                }
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -390,6 +425,10 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
     DM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "row strides must be multiples of 8 elements (16 bytes)");
     DM_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "16-byte aligned operands");
     if (batch < 1) batch = 1;
+    if (ep && ep->act == 3) {
+        DM_REQUIRE(N % 64 == 0 && ldc % 8 == 0 && !ep->residual && !ep->rowvec && !ep->out_f32,
+                   "GEGLU epilogue: N multiple of 64 (interleaved value/gate rows), 16-bit output of N/2 columns");
+    }
     int bn = pick_bn((int64_t)M * (batch > 1 ? batch : 1), N, bn_hint);
     CUtensorMap tmA, tmB;
     {

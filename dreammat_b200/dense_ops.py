@@ -15,7 +15,7 @@ class Epilogue(C.Structure):
                 ("alpha", C.c_float), ("out_scale", C.c_float), ("act", C.c_int32), ("out_f32", C.c_int32)]
 
 
-ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2}
+ACT = {None: 0, "none": 0, "silu": 1, "gelu": 2, "geglu": 3}
 
 
 def _ep(bias=None, rowvec=None, rows_per_vec=1, residual=None, ld_res=0, res_batch_stride=0, alpha=1.0, out_scale=1.0,
@@ -58,7 +58,8 @@ def gemm(a, b, bias=None, rowvec=None, rows_per_vec=1, residual=None, alpha=1.0,
     a_bs = a.stride(0) if batched else 0
     b_bs = b.stride(0) if b.dim() == 3 else 0
     if out is None:
-        shape = (batch, M, N) if batched else (M, N)
+        n_out = N // 2 if act == "geglu" else N      # GEGLU epilogue: value * gelu(gate), see geglu_interleave
+        shape = (batch, M, n_out) if batched else (M, n_out)
         out = torch.empty(shape, device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     assert out.stride(-1) == 1
     ldc = out.stride(-2)
@@ -155,6 +156,15 @@ def layernorm(x, gamma, beta, eps=1e-5):
     check(lib().dm_layernorm(bf, ptr_any(x), M, Cc, ptr_any(gamma), ptr_any(beta), eps, ptr_any(y), stream_ptr()),
           "dm_layernorm")
     return y
+
+
+def geglu_interleave(w):
+    """Row order the fused GEGLU epilogue of dm_gemm expects: [value | gate] halves (diffusers GEGLU.proj,
+    attention.py chunk(2, dim=-1)) -> alternating blocks of 32 value rows and their 32 gate rows."""
+    D = w.shape[0] // 2
+    assert D % 32 == 0
+    v, g = w[:D].reshape(D // 32, 1, 32, *w.shape[1:]), w[D:].reshape(D // 32, 1, 32, *w.shape[1:])
+    return torch.cat([v, g], 1).reshape(w.shape).contiguous()
 
 
 def geglu(h):

@@ -94,6 +94,8 @@ class _UNetCommon(_Base):
                                               0).float().to(self.dev, self.dt).contiguous()
         self._lin(b + ".attn2.to_out.0")
         self._lin(b + ".ff.net.0.proj"); self._lin(b + ".ff.net.2")
+        for k in (".w", ".bias"):      # value/gate rows interleaved for the fused GEGLU epilogue
+            self.p[b + ".ff.net.0.proj" + k] = D.geglu_interleave(self.p[b + ".ff.net.0.proj" + k])
 
     def _prep_encoder_half(self):
         cfg = self.cfg
@@ -163,8 +165,7 @@ class _UNetCommon(_Base):
         o = D.attention(q, kv[..., :C], kv[..., C:], heads)
         h = D.gemm(o.view(M, C), P[b + ".attn2.to_out.0.w"], bias=P[b + ".attn2.to_out.0.bias"], residual=h)
         n3 = D.layernorm(h, P[b + ".norm3.weight"], P[b + ".norm3.bias"])
-        g = D.gemm(n3, P[b + ".ff.net.0.proj.w"], bias=P[b + ".ff.net.0.proj.bias"])
-        f = D.geglu(g)
+        f = D.gemm(n3, P[b + ".ff.net.0.proj.w"], bias=P[b + ".ff.net.0.proj.bias"], act="geglu")
         h = D.gemm(f, P[b + ".ff.net.2.w"], bias=P[b + ".ff.net.2.bias"], residual=h)
         xs = x if x.is_contiguous() else x.contiguous()
         return D.gemm(h, P[p + ".proj_out.w"], bias=P[p + ".proj_out.bias"], residual=xs.view(M, C)).view(n, H, W, C)

@@ -105,6 +105,15 @@ class DreamMatMesh:
 
     __call__ = forward
 
+    def export(self, points: torch.Tensor, **kwargs) -> Dict[str, Any]:
+        """dreammat_mesh.py:256-274: features at the (unscaled) query points for the texture bake; no graph."""
+        if self.cfg.n_feature_dims == 0:
+            return {}
+        pts = points.reshape(-1, 3).to(self.device, torch.float32).contiguous()
+        with torch.no_grad():
+            f = R.hashgrid_mlp(pts, self.grid, self.W1, self.W2, self.hg)
+        return {"features": f.view(*points.shape[:-1], self.cfg.n_feature_dims)}
+
     # ---- checkpoint compatibility (SURVEY.md section 5 / 8f N2): same keys, shapes and tcnn parameter order as the
     # reference's `geometry.*` entries, so a Lightning .ckpt written by either side loads into the other
     def state_dict(self, prefix: str = ""):
@@ -173,6 +182,19 @@ class DreamMatMaterial:
         self.FG_LUT = fg_lut.to(self.device).contiguous() if fg_lut is not None else None
         self.envlight = envlight  # [(diffuse_cube, [spec mips])] per env (split-sum branch)
         self.bvh = None
+
+    def export(self, features: torch.Tensor, **kwargs) -> Dict[str, Any]:
+        """dreammat_material.py:765-797: baked maps use the *squared*-roughness range and sqrt(. + 1e-7); the bump
+        slot reads channels 5:8, which exist only when the geometry is configured with n_feature_dims >= 8."""
+        c = self.cfg
+        m = torch.sigmoid(features)
+        out = {"albedo": m[..., :3],
+               "metallic": m[..., 3:4] * (c.max_metallic - c.min_metallic) + c.min_metallic,
+               "roughness": torch.sqrt(m[..., 4:5] * (c.max_roughness_squre - c.min_roughness_squre) + c.min_roughness_squre + 1e-7)}
+        if c.use_bump and m.shape[-1] >= 8:
+            pn = (m[..., 5:8] * 2 - 1) + torch.tensor([0.0, 0.0, 1.0], dtype=m.dtype, device=m.device)
+            out["bump"] = (torch.nn.functional.normalize(pn.clamp(-1, 1), dim=-1) + 1) / 2
+        return out
 
     def set_raytracer(self, bvh):
         """dreammat_material.py:426-427; here the tracer is the device BVH handle."""

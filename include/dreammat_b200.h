@@ -191,7 +191,8 @@ typedef struct {
     int64_t res_batch_stride;
     float alpha;
     float out_scale;
-    int32_t act;               /* 0 none, 1 SiLU, 2 GELU(erf) */
+    int32_t act;               /* 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: B rows interleaved [32 value | 32 gate],
+                                * C gets N/2 columns value*gelu(gate) (attention.py GEGLU of the FF block) */
     int32_t out_f32;           /* 1: C is float32 */
 } dm_epilogue;
 

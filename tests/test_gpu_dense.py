@@ -60,6 +60,18 @@ def test_gemm_conv_match_torch_fp32():
     assert rel(nchw(y), ref) < 1e-3
     with pytest.raises(Exception):
         D.gemm(a[:, :100].contiguous(), b[:, :100].contiguous())  # K % 64 != 0 must fail loudly
+    # fused GEGLU epilogue (diffusers attention.py GEGLU: hidden, gate = proj(x).chunk(2); hidden * gelu(gate))
+    for M, Dh in ((300, 256), (4096, 1280), (150, 64)):
+        for bn in (0, 64, 128, 256):
+            if bn > 2 * Dh:
+                continue
+            a = torch.randn(M, 192, device="cuda", generator=g).half()
+            w = (torch.randn(2 * Dh, 192, device="cuda", generator=g) / 14).half()
+            bias = torch.randn(2 * Dh, device="cuda", generator=g).half()
+            out = D.gemm(a, D.geglu_interleave(w), bias=D.geglu_interleave(bias), act="geglu", bn=bn)
+            pr = a.float() @ w.float().t() + bias.float()
+            ref = pr[:, :Dh] * F.gelu(pr[:, Dh:])
+            assert out.shape == (M, Dh) and rel(out, ref) < 1e-3, (M, Dh, bn, rel(out, ref))
 
 
 def test_attention_matches_torch_fp32():

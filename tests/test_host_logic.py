@@ -109,3 +109,19 @@ def test_geometry_checkpoint_keys_and_layout():
     assert float(geo.params.min()) == 0.5 == float(geo.params.max())  # the views alias the one flat buffer
     with pytest.raises(ValueError):
         geo.load_state_dict({k: v[:-1] if v.dim() == 1 else v for k, v in ck.items()})
+
+
+def test_material_export_matches_reference_formula():
+    """N2: dreammat_material.py:765-797 — bake-time maps use the squared-roughness range and sqrt(r2 + 1e-7)."""
+    from dreammat_b200.system import DreamMatMaterial
+    mat = DreamMatMaterial({}, "cpu")
+    f = torch.randn(7, 5, generator=torch.Generator().manual_seed(0))
+    out = mat.export(f)
+    m = torch.sigmoid(f)
+    assert set(out) == {"albedo", "metallic", "roughness"}
+    assert torch.equal(out["albedo"], m[:, :3])
+    assert torch.allclose(out["metallic"], m[:, 3:4] * 0.9)
+    assert torch.allclose(out["roughness"], torch.sqrt(m[:, 4:5] * 0.89 + 0.01 + 1e-7))
+    f8 = torch.randn(7, 8, generator=torch.Generator().manual_seed(1))
+    b = mat.export(f8)["bump"]
+    assert b.shape == (7, 3) and float(b.min()) >= 0 and float(b.max()) <= 1
