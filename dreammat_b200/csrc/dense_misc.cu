@@ -30,223 +30,254 @@ template <> struct H<__nv_bfloat16> {
         else { using T = __half; __VA_ARGS__; }                   \
     } while (0)
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float silu_grad(float x) {
-    float s = 1.0f / (1.0f + __expf(-x));
+    float s = __fdividef(1.0f, 1.0f + __expf(-x));
     return s * (1.0f + x * (1.0f - s));
 }
 
 // ----------------------------------------------------------------------------------- GroupNorm
-// stats[(img*G + g)*2 + {0,1}] += (sum, sumsq) over the group's channels and the pixel chunk.
-// One thread owns one 8-channel vector (16 B) and strides over pixels with 4 independent loads in flight;
-// channel PAIRS never straddle a group (cpg is even for every SD layer), so each thread keeps 4 (sum, sumsq)
-// pairs and folds them into the block's shared accumulators once.
+// Thread mapping shared by the four kernels: the channel axis is cut into slabs of `vslab` 8-channel vectors
+// (vslab = largest divisor of C/8 that is <= 32, i.e. 512 contiguous bytes per pixel), grid = (pixel chunks,
+// images, slabs).  A thread owns ONE vector of the slab and strides over the chunk's pixels with `lanes` =
+// blockDim / vslab pixel lanes, so per-channel constants live in registers and the loop body is pure
+// load / FMA / store with several 16-byte loads in flight.  Small feature maps (8x8 .. 32x32 latents) get their
+// parallelism from the slab axis instead of idling most of the machine.
+struct GnIdx {
+    int v, q, lanes, p0, p1;
+    bool active;
+};
+__device__ __forceinline__ GnIdx gn_index(int HW, int vslab, int chunks) {
+    GnIdx m;
+    m.lanes = (int)blockDim.x / vslab;
+    m.q = (int)threadIdx.x / vslab;
+    m.v = (int)blockIdx.z * vslab + (int)threadIdx.x % vslab;
+    m.active = m.q < m.lanes;
+    const int px_per_chunk = (HW + chunks - 1) / chunks;
+    m.p0 = (int)blockIdx.x * px_per_chunk;
+    m.p1 = min(HW, m.p0 + px_per_chunk);
+    return m;
+}
+
+// stats[(img*G + g)*2 + {0,1}] += (sum, sumsq) over the group's channels and the pixel chunk.  Channel PAIRS never
+// straddle a group (cpg is even for every SD layer), so each thread keeps 4 (sum, sumsq) pairs.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int G,
-                                                       int chunks, float* __restrict__ stats) {
+                                                       int chunks, int vslab, float* __restrict__ stats) {
     extern __shared__ float s_acc[];  // [G*2]
-    const int img = blockIdx.y, chunk = blockIdx.x;
-    const int vpp = C / 8, cpg = C / G;
+    const int img = blockIdx.y, cpg = C / G;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    const int px_per_chunk = (HW + chunks - 1) / chunks;
-    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / vpp);
-    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
-    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
+    const GnIdx m = gn_index(HW, vslab, chunks);
+    if (m.active) {
         float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-        const T* base = x + ((int64_t)img * HW) * ld + 8 * v;
-        int p = p0 + q;
-        for (; p + 3 * lanes < p1; p += 4 * lanes) {
-            uint4 u[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (int64_t)(p + k * lanes) * ld);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const T* h = reinterpret_cast<const T*>(&u[k]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a = H<T>::f(h[2 * j]), b = H<T>::f(h[2 * j + 1]);
-                    s[j] += a + b; ss[j] += a * a + b * b;
-                }
-            }
-        }
-        for (; p < p1; p += lanes) {
-            uint4 u = *reinterpret_cast<const uint4*>(base + (int64_t)p * ld);
+        const T* base = x + ((int64_t)img * HW) * ld + 8 * m.v;
+        const int lanes = m.lanes;
+        auto acc = [&](const uint4& u) {
             const T* h = reinterpret_cast<const T*>(&u);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float a = H<T>::f(h[2 * j]), b = H<T>::f(h[2 * j + 1]);
                 s[j] += a + b; ss[j] += a * a + b * b;
             }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int g = (8 * v + 2 * j) / cpg;
-            atomicAdd(&s_acc[2 * g], s[j]); atomicAdd(&s_acc[2 * g + 1], ss[j]);
-        }
-        if (vpp <= (int)blockDim.x) break;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + ((int64_t)img * G) * 2 + i, s_acc[i]);
-}
-
-// y = act(x * A[c] + B[c]) with A = rstd*gamma, B = beta - mean*rstd*gamma.  Same thread mapping as the stats
-// kernel (one fixed 8-channel vector per thread, striding over pixels), so A/B live in 16 registers and the
-// loop body is load-16B / 8 FMA (+SiLU) / store-16B with 4 independent loads in flight.
-template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int HW, int C, int ld, int ldy, int G,
-                                                       int chunks, const float* __restrict__ stats,
-                                                       const T* __restrict__ gamma, const T* __restrict__ beta,
-                                                       float eps, int silu, T* __restrict__ y) {
-    const int img = blockIdx.y, chunk = blockIdx.x;
-    const int vpp = C / 8, cpg = C / G;
-    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    const int px_per_chunk = (HW + chunks - 1) / chunks;
-    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / vpp);
-    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
-    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
-        float A[8], Bc[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int g = (8 * v + 2 * j) / cpg;
-            float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
-            float mean = s * inv_cnt, rstd = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float gm = H<T>::f(gamma[8 * v + 2 * j + k]);
-                A[2 * j + k] = rstd * gm;
-                Bc[2 * j + k] = H<T>::f(beta[8 * v + 2 * j + k]) - mean * rstd * gm;
-            }
-        }
-        const T* xb = x + ((int64_t)img * HW) * ld + 8 * v;
-        T* yb = y + ((int64_t)img * HW) * ldy + 8 * v;
-        auto body = [&](uint4 u, int p) {
-            const T* h = reinterpret_cast<const T*>(&u);
-            uint4 o; T* oh = reinterpret_cast<T*>(&o);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float val = fmaf(H<T>::f(h[k]), A[k], Bc[k]);
-                if (silu) val = silu_f(val);
-                oh[k] = H<T>::t(val);
-            }
-            *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = o;
         };
-        int p = p0 + q;
-        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        int p = m.p0 + m.q;
+        for (; p + 3 * lanes < m.p1; p += 4 * lanes) {
             uint4 u[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + k * lanes) * ld);
+            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (int64_t)(p + k * lanes) * ld);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) body(u[k], p + k * lanes);
+            for (int k = 0; k < 4; ++k) acc(u[k]);
         }
-        for (; p < p1; p += lanes) body(*reinterpret_cast<const uint4*>(xb + (int64_t)p * ld), p);
-        if (vpp <= (int)blockDim.x) break;
+        for (; p < m.p1; p += lanes) acc(*reinterpret_cast<const uint4*>(base + (int64_t)p * ld));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int g = (8 * m.v + 2 * j) / cpg;
+            atomicAdd(&s_acc[2 * g], s[j]); atomicAdd(&s_acc[2 * g + 1], ss[j]);
+        }
     }
+    __syncthreads();
+    // only the groups this slab touches
+    const int g0 = (8 * (int)blockIdx.z * vslab) / cpg, g1 = (8 * ((int)blockIdx.z + 1) * vslab - 1) / cpg;
+    for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(stats + ((int64_t)img * G) * 2 + i, s_acc[i]);
+}
+
+// y = act(x * A[c] + B[c]) with A = rstd*gamma, B = beta - mean*rstd*gamma (16 registers per thread).
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int HW, int C, int ld, int ldy, int G,
+                                                       int chunks, int vslab, const float* __restrict__ stats,
+                                                       const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                       float eps, int silu, T* __restrict__ y) {
+    const int img = blockIdx.y, cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    const GnIdx m = gn_index(HW, vslab, chunks);
+    if (!m.active) return;
+    const int v = m.v, lanes = m.lanes;
+    float A[8], Bc[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int g = (8 * v + 2 * j) / cpg;
+        float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
+        float mean = s * inv_cnt, rstd = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float gm = H<T>::f(gamma[8 * v + 2 * j + k]);
+            A[2 * j + k] = rstd * gm;
+            Bc[2 * j + k] = H<T>::f(beta[8 * v + 2 * j + k]) - mean * rstd * gm;
+        }
+    }
+    const T* xb = x + ((int64_t)img * HW) * ld + 8 * v;
+    T* yb = y + ((int64_t)img * HW) * ldy + 8 * v;
+    auto body = [&](uint4 u, int p) {
+        const T* h = reinterpret_cast<const T*>(&u);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float val = fmaf(H<T>::f(h[k]), A[k], Bc[k]);
+            if (silu) val = silu_f(val);
+            oh[k] = H<T>::t(val);
+        }
+        *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = o;
+    };
+    int p = m.p0 + m.q;
+    for (; p + 3 * lanes < m.p1; p += 4 * lanes) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (int64_t)(p + k * lanes) * ld);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) body(u[k], p + k * lanes);
+    }
+    for (; p < m.p1; p += lanes) body(*reinterpret_cast<const uint4*>(xb + (int64_t)p * ld), p);
 }
 
 // backward pass 1: bstats[(img*G+g)*2] += sum(gamma*dy'), += sum(gamma*dy'*xhat), dy' = dz * act'(y)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dz, int HW,
-                                                           int C, int G, int chunks, const float* __restrict__ stats,
-                                                           const T* __restrict__ gamma, const T* __restrict__ beta,
-                                                           float eps, int silu, float* __restrict__ bstats) {
+                                                           int C, int G, int chunks, int vslab,
+                                                           const float* __restrict__ stats, const T* __restrict__ gamma,
+                                                           const T* __restrict__ beta, float eps, int silu,
+                                                           float* __restrict__ bstats) {
     extern __shared__ float s_acc[];
-    const int img = blockIdx.y, chunk = blockIdx.x, cpg = C / G, vpp = C / 8;
+    const int img = blockIdx.y, cpg = C / G;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    const int px_per_chunk = (HW + chunks - 1) / chunks;
-    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / vpp);
-    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
-    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
-        float mean[4], rstd[4], gm[8], bt[8], a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    const GnIdx m = gn_index(HW, vslab, chunks);
+    if (m.active) {
+        const int v = m.v, lanes = m.lanes;
+        // xhat*gamma + beta = x*A + Bc;  xhat = x*rs + ms
+        float A[8], Bc[8], gm[8], rs[4], ms[4], a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int g = (8 * v + 2 * j) / cpg;
             float s = stats[((int64_t)img * G + g) * 2], ss = stats[((int64_t)img * G + g) * 2 + 1];
-            mean[j] = s * inv_cnt;
-            rstd[j] = rsqrtf(fmaxf(ss * inv_cnt - mean[j] * mean[j], 0.f) + eps);
+            float mean = s * inv_cnt;
+            rs[j] = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
+            ms[j] = -mean * rs[j];
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { gm[k] = H<T>::f(gamma[8 * v + k]); bt[k] = H<T>::f(beta[8 * v + k]); }
+        for (int k = 0; k < 8; ++k) {
+            gm[k] = H<T>::f(gamma[8 * v + k]);
+            A[k] = rs[k >> 1] * gm[k];
+            Bc[k] = H<T>::f(beta[8 * v + k]) + ms[k >> 1] * gm[k];
+        }
         const int64_t base = ((int64_t)img * HW) * C + 8 * v;
-        for (int p = p0 + q; p < p1; p += lanes) {
-            uint4 ux = *reinterpret_cast<const uint4*>(x + base + (int64_t)p * C);
-            uint4 ud = *reinterpret_cast<const uint4*>(dz + base + (int64_t)p * C);
+        auto acc = [&](const uint4& ux, const uint4& ud) {
             const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float xh = (H<T>::f(hx[k]) - mean[k >> 1]) * rstd[k >> 1];
-                float d = H<T>::f(hd[k]);
-                if (silu) d *= silu_grad(xh * gm[k] + bt[k]);
-                a1[k >> 1] += gm[k] * d;
-                a2[k >> 1] += gm[k] * d * xh;
+                float xv = H<T>::f(hx[k]);
+                float d = H<T>::f(hd[k]) * gm[k];
+                if (silu) d *= silu_grad(fmaf(xv, A[k], Bc[k]));
+                a1[k >> 1] += d;
+                a2[k >> 1] = fmaf(d, fmaf(xv, rs[k >> 1], ms[k >> 1]), a2[k >> 1]);
             }
+        };
+        int p = m.p0 + m.q;
+        for (; p + lanes < m.p1; p += 2 * lanes) {
+            uint4 ux0 = *reinterpret_cast<const uint4*>(x + base + (int64_t)p * C);
+            uint4 ud0 = *reinterpret_cast<const uint4*>(dz + base + (int64_t)p * C);
+            uint4 ux1 = *reinterpret_cast<const uint4*>(x + base + (int64_t)(p + lanes) * C);
+            uint4 ud1 = *reinterpret_cast<const uint4*>(dz + base + (int64_t)(p + lanes) * C);
+            acc(ux0, ud0); acc(ux1, ud1);
         }
+        for (; p < m.p1; p += lanes)
+            acc(*reinterpret_cast<const uint4*>(x + base + (int64_t)p * C), *reinterpret_cast<const uint4*>(dz + base + (int64_t)p * C));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int g = (8 * v + 2 * j) / cpg;
             atomicAdd(&s_acc[2 * g], a1[j]); atomicAdd(&s_acc[2 * g + 1], a2[j]);
         }
-        if (vpp <= (int)blockDim.x) break;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(bstats + ((int64_t)img * G) * 2 + i, s_acc[i]);
+    const int g0 = (8 * (int)blockIdx.z * vslab) / cpg, g1 = (8 * ((int)blockIdx.z + 1) * vslab - 1) / cpg;
+    for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(bstats + ((int64_t)img * G) * 2 + i, s_acc[i]);
 }
 
 // backward pass 2: dx = rstd * (gamma*dy' - (S1 + xhat*S2)/cnt)  (+ dx_add if given); same mapping as gn_apply
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dz, int HW,
-                                                           int C, int G, int chunks, const float* __restrict__ stats,
-                                                           const float* __restrict__ bstats,
+                                                           int C, int G, int chunks, int vslab,
+                                                           const float* __restrict__ stats, const float* __restrict__ bstats,
                                                            const T* __restrict__ gamma, const T* __restrict__ beta,
                                                            float eps, int silu, const T* __restrict__ dx_add,
                                                            T* __restrict__ dx) {
-    const int img = blockIdx.y, chunk = blockIdx.x;
-    const int vpp = C / 8, cpg = C / G;
+    const int img = blockIdx.y, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    const int px_per_chunk = (HW + chunks - 1) / chunks;
-    const int p0 = chunk * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
-    const int lanes = max(1, (int)blockDim.x / vpp);
-    const int q = (vpp <= (int)blockDim.x) ? (int)threadIdx.x / vpp : 0;
-    for (int v = (vpp <= (int)blockDim.x) ? (int)threadIdx.x % vpp : (int)threadIdx.x; v < vpp && q < lanes; v += blockDim.x) {
-        float mean[4], rstd[4], S1[4], S2[4], gm[8], bt[8];
+    const GnIdx m = gn_index(HW, vslab, chunks);
+    if (!m.active) return;
+    const int v = m.v, lanes = m.lanes;
+    // act'(y) needs y = x*A + Bc (A = rs*gm, Bc = beta + ms*gm, ms = -mean*rs); with xhat = x*rs + ms
+    // dx = rs*(gm*d' - S1 - xhat*S2) = d'*A - (x*P + Q),  P = rs^2*S2,  Q = rs*(S1 + ms*S2)
+    float A[8], Bc[8], rs[4], ms[4], Pq[4], Qq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int g = (8 * v + 2 * j) / cpg;
-            int64_t si = ((int64_t)img * G + g) * 2;
-            float s = stats[si], ss = stats[si + 1];
-            mean[j] = s * inv_cnt;
-            rstd[j] = rsqrtf(fmaxf(ss * inv_cnt - mean[j] * mean[j], 0.f) + eps);
-            S1[j] = bstats[si] * inv_cnt; S2[j] = bstats[si + 1] * inv_cnt;
+    for (int j = 0; j < 4; ++j) {
+        int g = (8 * v + 2 * j) / cpg;
+        int64_t si = ((int64_t)img * G + g) * 2;
+        float s = stats[si], ss = stats[si + 1];
+        float mean = s * inv_cnt;
+        rs[j] = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
+        ms[j] = -mean * rs[j];
+        float S1 = bstats[si] * inv_cnt, S2 = bstats[si + 1] * inv_cnt;
+        Pq[j] = rs[j] * rs[j] * S2;
+        Qq[j] = rs[j] * (S1 + ms[j] * S2);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float gm = H<T>::f(gamma[8 * v + k]);
+        A[k] = rs[k >> 1] * gm;
+        Bc[k] = H<T>::f(beta[8 * v + k]) + ms[k >> 1] * gm;
+    }
+    const int64_t base = ((int64_t)img * HW) * C + 8 * v;
+    auto body = [&](const uint4& ux, const uint4& ud, const uint4& ua, int64_t off) {
+        const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
+        const T* ha = reinterpret_cast<const T*>(&ua);
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xv = H<T>::f(hx[k]);
+            float d = H<T>::f(hd[k]);
+            if (silu) d *= silu_grad(fmaf(xv, A[k], Bc[k]));
+            float val = fmaf(d, A[k], -fmaf(xv, Pq[k >> 1], Qq[k >> 1]));
+            if (dx_add) val += H<T>::f(ha[k]);
+            oh[k] = H<T>::t(val);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { gm[k] = H<T>::f(gamma[8 * v + k]); bt[k] = H<T>::f(beta[8 * v + k]); }
-        const int64_t base = ((int64_t)img * HW) * C + 8 * v;
-        for (int p = p0 + q; p < p1; p += lanes) {
-            const int64_t off = base + (int64_t)p * C;
-            uint4 ux = *reinterpret_cast<const uint4*>(x + off);
-            uint4 ud = *reinterpret_cast<const uint4*>(dz + off);
-            uint4 ua = make_uint4(0, 0, 0, 0);
-            if (dx_add) ua = *reinterpret_cast<const uint4*>(dx_add + off);
-            const T* hx = reinterpret_cast<const T*>(&ux); const T* hd = reinterpret_cast<const T*>(&ud);
-            const T* ha = reinterpret_cast<const T*>(&ua);
-            uint4 o; T* oh = reinterpret_cast<T*>(&o);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float xh = (H<T>::f(hx[k]) - mean[k >> 1]) * rstd[k >> 1];
-                float d = H<T>::f(hd[k]);
-                if (silu) d *= silu_grad(xh * gm[k] + bt[k]);
-                float val = rstd[k >> 1] * (gm[k] * d - S1[k >> 1] - xh * S2[k >> 1]);
-                if (dx_add) val += H<T>::f(ha[k]);
-                oh[k] = H<T>::t(val);
-            }
-            *reinterpret_cast<uint4*>(dx + off) = o;
-        }
-        if (vpp <= (int)blockDim.x) break;
+        *reinterpret_cast<uint4*>(dx + off) = o;
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    int p = m.p0 + m.q;
+    for (; p + lanes < m.p1; p += 2 * lanes) {
+        const int64_t o0 = base + (int64_t)p * C, o1 = base + (int64_t)(p + lanes) * C;
+        uint4 ux0 = *reinterpret_cast<const uint4*>(x + o0), ud0 = *reinterpret_cast<const uint4*>(dz + o0);
+        uint4 ux1 = *reinterpret_cast<const uint4*>(x + o1), ud1 = *reinterpret_cast<const uint4*>(dz + o1);
+        uint4 ua0 = dx_add ? *reinterpret_cast<const uint4*>(dx_add + o0) : zero;
+        uint4 ua1 = dx_add ? *reinterpret_cast<const uint4*>(dx_add + o1) : zero;
+        body(ux0, ud0, ua0, o0); body(ux1, ud1, ua1, o1);
+    }
+    for (; p < m.p1; p += lanes) {
+        const int64_t o0 = base + (int64_t)p * C;
+        body(*reinterpret_cast<const uint4*>(x + o0), *reinterpret_cast<const uint4*>(dz + o0),
+             dx_add ? *reinterpret_cast<const uint4*>(dx_add + o0) : zero, o0);
     }
 }
 
@@ -500,10 +531,15 @@ inline int grid_for(int64_t work, int threads = 256) {
     int64_t cap = (int64_t)DM_NUM_SMS * 8;
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
-inline int gn_chunks(int n_img, int HW) {
-    int c = (DM_NUM_SMS * 8) / (n_img > 0 ? n_img : 1);
+inline int gn_vslab(int vpp) {
+    for (int d = 32; d > 1; --d) if (vpp % d == 0) return d;
+    return 1;
+}
+// pixel chunks so that chunks * n_img * slabs ~ 8 CTAs per SM, each thread keeping >= 4 pixels to stream
+inline int gn_chunks(int n_img, int HW, int slabs, int lanes) {
+    int c = (DM_NUM_SMS * 8) / ((n_img > 0 ? n_img : 1) * slabs);
     if (c < 1) c = 1;
-    int maxc = HW / 64; if (maxc < 1) maxc = 1;
+    int maxc = HW / (4 * lanes); if (maxc < 1) maxc = 1;
     return c < maxc ? c : maxc;
 }
 
@@ -515,12 +551,13 @@ extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, i
     DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0 && ld % 8 == 0 && ldy % 8 == 0, "channel layout");
     cudaStream_t st = (cudaStream_t)stream;
     DM_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n_img * G, st));
-    int chunks = gn_chunks(n_img, HW);
-    int threads = 256;
-    DM_DISPATCH_T(bf16, gn_stats_kernel<T><<<dim3(chunks, n_img), threads, 2 * G * sizeof(float), st>>>((const T*)x, HW, C, ld, G, chunks, stats));
+    const int vslab = gn_vslab(C / 8), slabs = (C / 8) / vslab;
+    const int chunks = gn_chunks(n_img, HW, slabs, 256 / vslab);
+    const dim3 grid(chunks, n_img, slabs);
+    DM_DISPATCH_T(bf16, gn_stats_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>((const T*)x, HW, C, ld, G, chunks, vslab, stats));
     DM_CHECK_LAUNCH();
-    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<dim3(chunks, n_img), 256, 0, st>>>((const T*)x, HW, C, ld, ldy, G, chunks, stats, (const T*)gamma,
-                                                                             (const T*)beta, eps, silu, (T*)y));
+    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, HW, C, ld, ldy, G, chunks, vslab, stats, (const T*)gamma,
+                                                                (const T*)beta, eps, silu, (T*)y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -532,13 +569,15 @@ extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_i
     DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0, "channel layout");
     cudaStream_t st = (cudaStream_t)stream;
     DM_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * n_img * G, st));
-    int chunks = gn_chunks(n_img, HW);
-    DM_DISPATCH_T(bf16, gn_bwd_stats_kernel<T><<<dim3(chunks, n_img), 256, 2 * G * sizeof(float), st>>>(
-                            (const T*)x, (const T*)dz, HW, C, G, chunks, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats));
+    const int vslab = gn_vslab(C / 8), slabs = (C / 8) / vslab;
+    const int chunks = gn_chunks(n_img, HW, slabs, 256 / vslab);
+    const dim3 grid(chunks, n_img, slabs);
+    DM_DISPATCH_T(bf16, gn_bwd_stats_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>(
+                            (const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats));
     DM_CHECK_LAUNCH();
-    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<dim3(chunks, n_img), 256, 0, st>>>((const T*)x, (const T*)dz, HW, C, G, chunks, stats, bstats,
-                                                                                 (const T*)gamma, (const T*)beta, eps, silu,
-                                                                                 (const T*)dx_add, (T*)dx));
+    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats, bstats,
+                                                                    (const T*)gamma, (const T*)beta, eps, silu,
+                                                                    (const T*)dx_add, (T*)dx));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

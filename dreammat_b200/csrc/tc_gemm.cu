@@ -60,6 +60,129 @@ template <> struct Cvt<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
+// Epilogue of one 128-row accumulator tile: this warp's 32 TMEM lanes (one output row per thread), BN columns in
+// chunks of 32: acc*alpha + bias + rowvec -> act -> + residual -> * out_scale -> 16-byte stores.  `release_bar` is
+// arrived on (once per warp) as soon as the last chunk sits in registers, handing the TMEM buffer back to the MMA
+// issuer; REMOTE = the barrier lives in the leader CTA of a pair (shared::cluster address).
+template <int BN, typename T, bool REMOTE>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int64_t m, int z, int n_tile,
+                                              int lane, uint32_t release_bar) {
+    const bool row_ok = m < p.M;
+    const T* bias = (const T*)p.bias;
+    const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
+    const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
+    char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
+    if (p.act == 3) {
+        // GEGLU epilogue: the weight rows come interleaved as [32 value | 32 gate] blocks (host side,
+        // dense_ops.geglu_interleave), so every 64 accumulator columns give 32 outputs value * gelu(gate)
+        // and the [M, N] projection never goes to HBM.  Output row length is N / 2.
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+            uint32_t v[32], g[32];
+            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c0 + 32), g);
+            tmem_ld_wait();
+            if (c0 + 64 >= BN) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+            }
+            const int n0 = n_tile * BN + c0;
+            if (!row_ok || n0 >= p.N) continue;
+            T* o = reinterpret_cast<T*>(outp) + (n0 >> 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                T* h = reinterpret_cast<T*>(&u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = q * 8 + j;
+                    float a = __uint_as_float(v[c]) * p.alpha, b = __uint_as_float(g[c]) * p.alpha;
+                    if (bias) { a += Cvt<T>::to_f(bias[n0 + c]); b += Cvt<T>::to_f(bias[n0 + 32 + c]); }
+                    h[j] = Cvt<T>::from_f(a * (0.5f * b * (1.0f + erff(b * 0.70710678118654752f))) * p.out_scale);
+                }
+                reinterpret_cast<uint4*>(o)[q] = u;
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+            // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+        }
+        const int n0 = n_tile * BN + c0;
+        if (!row_ok || n0 >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        const bool full = (n0 + 32 <= p.N);
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(bias[n0 + j]);
+        }
+        if (rowvec) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(rowvec[n0 + j]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+        } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+        }
+        if (res) {
+            if (full && ((p.ld_res & 7) == 0)) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(res + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u = r4[q];
+                    const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[q * 8 + j] += Cvt<T>::to_f(h[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += Cvt<T>::to_f(res[n0 + j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+        if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(outp) + n0;
+            if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = f[j];
+            }
+        } else {
+            T* o = reinterpret_cast<T*>(outp) + n0;
+            if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    T* h = reinterpret_cast<T*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = Cvt<T>::from_f(f[q * 8 + j]);
+                    reinterpret_cast<uint4*>(o)[q] = u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = Cvt<T>::from_f(f[j]);
+            }
+        }
+    }
+}
+
 // CPS = persistent CTAs per SM.  Two co-resident CTAs (each with its own single-thread MMA issuer and a ~96 KB operand
 // ring) keep the tensor pipe's queue fuller for the narrower tiles; 256-wide tiles need all of TMEM and run one per SM.
 template <int BN, int CPS> struct Cfg {
@@ -176,7 +299,6 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
         // ---------------------------------------------------- epilogue warps 2..5
         const int quarter = warp & 3;           // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;    // row inside the tile
-        const T* bias = (const T*)p.bias;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int z = t / tiles_per_z, r_ = t - z * tiles_per_z;
@@ -184,127 +306,154 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             const int64_t m = (int64_t)m_tile * BM + row;
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            const bool row_ok = m < p.M;
-            const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
-            const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
-            char* outp = (char*)p.out + ((int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc) * (p.out_f32 ? 4 : 2);
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
-            if (p.act == 3) {
-                // GEGLU epilogue: the weight rows come interleaved as [32 value | 32 gate] blocks (host side,
-                // dense_ops.geglu_interleave), so every 64 accumulator columns give 32 outputs value * gelu(gate)
-                // and the [M, N] projection never goes to HBM.  Output row length is N / 2.
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) {
-                    uint32_t v[32], g[32];
-                    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
-                    tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c0 + 32), g);
-                    tmem_ld_wait();
-                    if (c0 + 64 >= BN) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-                    }
-                    const int n0 = n_tile * BN + c0;
-                    if (!row_ok || n0 >= p.N) continue;
-                    T* o = reinterpret_cast<T*>(outp) + (n0 >> 1);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        T* h = reinterpret_cast<T*>(&u);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c = q * 8 + j;
-                            float a = __uint_as_float(v[c]) * p.alpha, b = __uint_as_float(g[c]) * p.alpha;
-                            if (bias) { a += Cvt<T>::to_f(bias[n0 + c]); b += Cvt<T>::to_f(bias[n0 + 32 + c]); }
-                            h[j] = Cvt<T>::from_f(a * (0.5f * b * (1.0f + erff(b * 0.70710678118654752f))) * p.out_scale);
-                        }
-                        reinterpret_cast<uint4*>(o)[q] = u;
-                    }
-                }
-                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
-                continue;
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (c0 + 32 >= BN) {
-                    // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-                }
-                const int n0 = n_tile * BN + c0;
-                if (!row_ok || n0 >= p.N) continue;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-                const bool full = (n0 + 32 <= p.N);
-                if (bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(bias[n0 + j]);
-                }
-                if (rowvec) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) f[j] += Cvt<T>::to_f(rowvec[n0 + j]);
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
-                } else if (p.act == 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
-                }
-                if (res) {
-                    if (full && ((p.ld_res & 7) == 0)) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(res + n0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 u = r4[q];
-                            const T* h = reinterpret_cast<const T*>(&u);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[q * 8 + j] += Cvt<T>::to_f(h[j]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += Cvt<T>::to_f(res[n0 + j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
-                if (p.out_f32) {
-                    float* o = reinterpret_cast<float*>(outp) + n0;
-                    if (full && ((p.ldc & 3) == 0)) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = f[j];
-                    }
-                } else {
-                    T* o = reinterpret_cast<T*>(outp) + n0;
-                    if (full && ((p.ldc & 7) == 0)) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 u;
-                            T* h = reinterpret_cast<T*>(&u);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) h[j] = Cvt<T>::from_f(f[q * 8 + j]);
-                            reinterpret_cast<uint4*>(o)[q] = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n0 + j < p.N) o[j] = Cvt<T>::from_f(f[j]);
-                    }
-                }
-            }
+            epilogue_tile<BN, T, false>(p, tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16), m, z, n_tile,
+                                        lane, tmem_empty_bar(acc));
             if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------- CTA-pair kernel
+// cta_group::2: the two CTAs of a cluster (one TPC) compute one 256 x BN tile.  Each CTA stages its own 128 rows of A
+// and HALF of the BN weight rows; the leader's single MMA thread issues 256 x BN x 16 instructions that read A from
+// both CTAs' shared memory and the B halves from both, and write rows 0-127 / 128-255 of the accumulator into the
+// two CTAs' TMEM.  Per MMA each SM reads A (4 KB) + B/2 instead of A + B, which lifts the shared-memory-bandwidth
+// bound the single-CTA 128-wide tiles run into, and every weight tile is fetched from L2 once per 256 rows.
+// Barriers: full[s] lives in the leader (both CTAs' TMA loads credit their bytes to it), empty[s] / tmem_full[a]
+// are arrived on in BOTH CTAs by multicast tcgen05.commit, tmem_empty[a] in the leader collects the 8 epilogue warps.
+template <int BN> struct PairCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 196608 / STAGE_BYTES;        // 6 (BN = 256) or 8 (BN = 128)
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM columns between the two accumulators
+    static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE;  // power of two (BN = 160 rounds up)
+};
+
+template <int BN, typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+    tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using C = PairCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int nk = p.K / BK;
+    const int n_tiles = (p.N + BN - 1) / BN, m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+    const int tiles_per_z = n_tiles * m_pairs;
+    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1);
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    cluster_sync_all();                                  // both CTAs' barriers exist before any remote arrive
+    if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    cluster_sync_all();                                  // the peer's TMEM is allocated before the first MMA lands in it
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer (both CTAs)
+            const int slabs = p.is_conv ? (p.Cin / BK) : nk;
+            const int tiles_w = p.is_conv ? p.Wo / p.tile_w : 1, tiles_h = p.is_conv ? p.Ho / p.tile_h : 1;
+            int stage = 0; uint32_t phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+                const int m_tile = (r / n_tiles) * 2 + (int)rank, n_tile = r % n_tiles;
+                int c_n = 0, c_h = 0, c_w = 0;
+                if (p.is_conv) {
+                    int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
+                    c_w = tw * p.tile_w * p.stride - p.pad_l;
+                    c_h = th * p.tile_h * p.stride - p.pad_t;
+                    c_n = tn * p.tile_n;                  // past the last image for a phantom tile: zero-filled
+                }
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + C::A_BYTES;
+                    const uint32_t lead_full = full_bar(stage) & PAIR_LEADER_MASK;
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    if (p.is_conv) {
+                        int tap = kb / slabs, slab = kb - tap * slabs;
+                        int kh = tap / p.kw_n, kw = tap - kh * p.kw_n;
+                        tma_load_4d_pair(a_dst, &tmA, lead_full, slab * BK, c_w + kw, c_h + kh, c_n);
+                    } else {
+                        tma_load_3d_pair(a_dst, &tmA, lead_full, kb * BK, m_tile * BM, z);
+                    }
+                    tma_load_3d_pair(b_dst, &tmB, lead_full, kb * BK, n_tile * BN + (int)rank * (BN / 2), p.b_batched ? z : 0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            // ------------------------------------------------ MMA issuer (one thread of the leader CTA)
+            constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
+            constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)((2 * BM) >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    umma_commit_pair(empty_bar(stage), 3);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_pair(tmem_full_bar(acc), 3);
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ---------------------------------------------------- epilogue warps 2..5 (both CTAs, own 128 rows)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+            const int z = t / tiles_per_z, r_ = t - z * tiles_per_z;
+            const int m_tile = (r_ / n_tiles) * 2 + (int)rank, n_tile = r_ % n_tiles;
+            const int64_t m = (int64_t)m_tile * BM + row;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_tile<BN, T, true>(p, tmem_base + (uint32_t)(acc * C::ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16), m, z, n_tile,
+                                       lane, tmem_empty_bar(acc) & PAIR_LEADER_MASK);
+            if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();          // nobody leaves (or frees TMEM) while the other CTA may still signal / be written
+    if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -371,7 +520,66 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     return launch_cps<BN, T, 1>(tmA, tmB, p, st);
 }
 
-int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st) {
+int g_gemm_pair = 1;  // 0 never, 1 where measured faster (use_pair), 2 wherever the shape allows (dm_tune_gemm 10/11/12)
+
+template <int BN, typename T>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+    static int max_clusters = 0;
+    auto kern = tc_gemm_pair_kernel<BN, T>;
+    if (!max_clusters) {
+        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<BN>::SMEM));
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(DM_NUM_SMS); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = PairCfg<BN>::SMEM;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = DM_NUM_SMS / 2; }
+        max_clusters = n < DM_NUM_SMS / 2 ? n : DM_NUM_SMS / 2;
+    }
+    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, 2 * BM) * (p.batch > 0 ? p.batch : 1);
+    unsigned clusters = (unsigned)(tiles < max_clusters ? tiles : max_clusters);
+    kern<<<2 * clusters, NTHREADS, PairCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+struct TileChoice { int bn; bool pair; };
+
+int pick_bn(int64_t M, int N, int bn_hint);
+
+// Tile width and single-CTA vs CTA-pair kernel.  bn_hint: 0 auto; 64/128/256 single-CTA kernel of that width;
+// 1000 + {128,160,256} CTA-pair kernel of that width (experiments / tests).
+TileChoice choose_tile(int64_t M, int N, int bn_hint, int act) {
+    if (bn_hint >= 1000) return {bn_hint - 1000, true};
+    if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return {bn_hint, g_gemm_pair == 2 && bn_hint >= 128};
+    if (g_gemm_pair) {
+        // wide pair tiles: every SM reads A + B/2 per MMA and each weight tile is fetched once per 256 rows.  Measured
+        // (scripts/sweep_tiles.py, profiles/r01_tile_sweep.md): 256-wide pairs beat the best single-CTA tile by 1.1-1.4x
+        // once there are >= 74 pair tiles (also for N = 640 / 960 / 1920 despite the padded last tile); 160-wide pairs
+        // (N = 320: two exact tiles) win by ~7 % but only with several waves of tiles.
+        const int64_t mp = dm_ceil_div(M, 2 * BM);
+        const int64_t tpcs = DM_NUM_SMS / 2;
+        if (N >= 512 || N == 256) {
+            if (mp * dm_ceil_div(N, 256) >= tpcs) return {256, true};
+        } else if (N % 160 == 0 && act != 3) {
+            if (mp * (N / 160) >= 3 * tpcs) return {160, true};
+        }
+    }
+    return {pick_bn(M, N, 0), false};
+}
+
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, bool pair, cudaStream_t st) {
+    if (pair) {
+        if (bf16) {
+            if (bn == 128) return launch_pair<128, __nv_bfloat16>(tmA, tmB, p, st);
+            if (bn == 160) return launch_pair<160, __nv_bfloat16>(tmA, tmB, p, st);
+            if (bn == 256) return launch_pair<256, __nv_bfloat16>(tmA, tmB, p, st);
+        } else {
+            if (bn == 128) return launch_pair<128, __half>(tmA, tmB, p, st);
+            if (bn == 160) return launch_pair<160, __half>(tmA, tmB, p, st);
+            if (bn == 256) return launch_pair<256, __half>(tmA, tmB, p, st);
+        }
+    }
     if (bf16) {
         if (bn == 64) return launch<64, __nv_bfloat16>(tmA, tmB, p, st);
         if (bn == 128) return launch<128, __nv_bfloat16>(tmA, tmB, p, st);
@@ -415,7 +623,11 @@ void fill_epilogue(GemmParams& p, const dm_epilogue* e, int N) {
 
 }  // namespace
 
-extern "C" int dm_tune_gemm(int ctas_per_sm) { g_gemm_cps = ctas_per_sm == 1 ? 1 : 2; return DM_OK; }
+extern "C" int dm_tune_gemm(int code) {
+    if (code >= 10 && code <= 12) g_gemm_pair = code - 10;      // CTA-pair kernel: 10 off, 11 heuristic, 12 always
+    else g_gemm_cps = code == 1 ? 1 : 2;                        // single-CTA kernel: persistent CTAs per SM
+    return DM_OK;
+}
 
 extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_stride, const void* B, int64_t ldb,
                        int64_t b_batch_stride, void* C, int64_t ldc, int64_t c_batch_stride, int M, int N, int K,
@@ -429,7 +641,11 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
         DM_REQUIRE(N % 64 == 0 && ldc % 8 == 0 && !ep->residual && !ep->rowvec && !ep->out_f32,
                    "GEGLU epilogue: N multiple of 64 (interleaved value/gate rows), 16-bit output of N/2 columns");
     }
-    int bn = pick_bn((int64_t)M * (batch > 1 ? batch : 1), N, bn_hint);
+    // batched GEMMs keep per-batch tiles; only the (possibly folded) batch-1 form pairs CTAs
+    TileChoice tc = (batch == 1) ? choose_tile(M, N, bn_hint, ep ? ep->act : 0)
+                                 : TileChoice{pick_bn((int64_t)M * batch, N, bn_hint >= 1000 ? 0 : bn_hint), false};
+    const int bn = tc.bn; const bool pair = tc.pair;
+    if (ep && ep->act == 3) DM_REQUIRE(bn % 64 == 0, "GEGLU epilogue needs a tile width that is a multiple of 64");
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
@@ -440,7 +656,7 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(b_batch_stride ? batch : 1)};
         uint64_t str[2] = {(uint64_t)ldb * 2, (uint64_t)(b_batch_stride ? b_batch_stride : (int64_t)N * ldb) * 2};
-        uint32_t box[3] = {BK, (uint32_t)bn, 1}, es[3] = {1, 1, 1};
+        uint32_t box[3] = {BK, (uint32_t)(pair ? bn / 2 : bn), 1}, es[3] = {1, 1, 1};
         int rc = encode_map(&tmB, bf16, B, 3, dims, str, box, es); if (rc) return rc;
     }
     if (batch > 1 && !b_batch_stride) {
@@ -454,7 +670,7 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
     p.M = M; p.N = N; p.K = K; p.batch = batch; p.b_batched = (batch > 1) ? 1 : 0; p.is_conv = 0;
     p.out = C; p.ldc = (int)ldc; p.out_batch_stride = c_batch_stride;
     fill_epilogue(p, ep, N);
-    return dispatch(tmA, tmB, p, bn, bf16, (cudaStream_t)stream);
+    return dispatch(tmA, tmB, p, bn, bf16, pair, (cudaStream_t)stream);
 }
 
 extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const void* w, int Cout, int ksize,
@@ -469,7 +685,8 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     int tile_n = BM / (tile_w * tile_h);
     DM_REQUIRE(tile_w * tile_h * tile_n == BM && Wo % tile_w == 0 && Ho % tile_h == 0,
                "output extent must tile into 128-pixel boxes (power-of-two sizes)");
-    int bn = pick_bn((int64_t)n_img * Ho * Wo, Cout, bn_hint);
+    TileChoice tc = choose_tile((int64_t)n_img * Ho * Wo, Cout, bn_hint, ep ? ep->act : 0);
+    const int bn = tc.bn; const bool pair = tc.pair;
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
@@ -482,7 +699,7 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)Cout, 1};
         uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * Cout * 2};
-        uint32_t box[3] = {BK, (uint32_t)bn, 1}, es[3] = {1, 1, 1};
+        uint32_t box[3] = {BK, (uint32_t)(pair ? bn / 2 : bn), 1}, es[3] = {1, 1, 1};
         int rc = encode_map(&tmB, bf16, w, 3, dims, str, box, es); if (rc) return rc;
     }
     GemmParams p; memset(&p, 0, sizeof(p));
@@ -490,5 +707,5 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     p.Ho = Ho; p.Wo = Wo; p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
     p.out = y; p.ldc = (int)ldc; p.out_batch_stride = 0;
     fill_epilogue(p, ep, Cout);
-    return dispatch(tmA, tmB, p, bn, bf16, (cudaStream_t)stream);
+    return dispatch(tmA, tmB, p, bn, bf16, pair, (cudaStream_t)stream);
 }
