@@ -48,6 +48,7 @@ struct GemmParams {
     float alpha;                            // applied to the accumulator first
     float out_scale;                        // applied last
     int act;                                // 0 none, 1 silu, 2 gelu(erf), 3 geglu (interleaved value|gate)
+    int split_k; float* ws;                 // split-K: fp32 partial sums are red.add'ed into ws[M, N]; splitk_finish_kernel applies the epilogue
 };
 
 template <typename T> struct Cvt;
@@ -68,6 +69,34 @@ template <int BN, typename T, bool REMOTE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int64_t m, int z, int n_tile,
                                               int lane, uint32_t release_bar) {
     const bool row_ok = m < p.M;
+    if (p.ws) {
+        // split-K partial tile: accumulate raw fp32 sums; the epilogue proper runs in splitk_finish_kernel
+        float* wrow = p.ws + ((int64_t)z * p.M + m) * p.N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (c0 + 32 >= BN) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+            }
+            const int n0 = n_tile * BN + c0;
+            if (!row_ok || n0 >= p.N) continue;
+            if (n0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    atomicAdd(reinterpret_cast<float4*>(wrow + n0) + q,
+                              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                          __uint_as_float(v[4 * q + 3])));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n0 + j < p.N) atomicAdd(wrow + n0 + j, __uint_as_float(v[j]));
+            }
+        }
+        return;
+    }
     const T* bias = (const T*)p.bias;
     const T* rowvec = p.rowvec ? (const T*)p.rowvec + (int64_t)(m / p.rows_per_vec) * p.ld_rowvec : nullptr;
     const T* res = p.residual ? (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res : nullptr;
@@ -218,7 +247,8 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
     const int nk = p.K / BK;
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM - 1) / BM;
     const int tiles_per_z = n_tiles * m_tiles;
-    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1);
+    const int S = p.split_k > 1 ? p.split_k : 1;       // split-K: S CTAs share an output tile, partial sums go to p.ws
+    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1) * S;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
@@ -240,8 +270,10 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             const int tiles_w = p.is_conv ? p.Wo / p.tile_w : 1, tiles_h = p.is_conv ? p.Ho / p.tile_h : 1;
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+                const int sp = t % S, tt = t / S;
+                const int z = tt / tiles_per_z, r = tt - z * tiles_per_z;
                 const int m_tile = r / n_tiles, n_tile = r - m_tile * n_tiles;
+                const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 int c_n = 0, c_h = 0, c_w = 0;
                 if (p.is_conv) {
                     int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
@@ -249,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
                     c_h = th * p.tile_h * p.stride - p.pad_t;
                     c_n = tn * p.tile_n;
                 }
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + C::A_BYTES;
@@ -275,10 +307,12 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int sp = t % S;
+                const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
@@ -286,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes along K inside the 128-byte swizzle atom = +2 in the (addr >> 4) field
-                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -301,7 +335,8 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
         const int row = quarter * 32 + lane;    // row inside the tile
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int z = t / tiles_per_z, r_ = t - z * tiles_per_z;
+            const int tt = t / S;
+            const int z = tt / tiles_per_z, r_ = tt - z * tiles_per_z;
             const int m_tile = r_ / n_tiles, n_tile = r_ - m_tile * n_tiles;
             const int64_t m = (int64_t)m_tile * BM + row;
             mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -354,7 +389,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     const int nk = p.K / BK;
     const int n_tiles = (p.N + BN - 1) / BN, m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
     const int tiles_per_z = n_tiles * m_pairs;
-    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1);
+    const int S = p.split_k > 1 ? p.split_k : 1;       // split-K over clusters, partial sums into p.ws
+    const int total_tiles = tiles_per_z * (p.batch > 0 ? p.batch : 1) * S;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -380,8 +416,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             const int tiles_w = p.is_conv ? p.Wo / p.tile_w : 1, tiles_h = p.is_conv ? p.Ho / p.tile_h : 1;
             int stage = 0; uint32_t phase = 0;
             for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-                const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+                const int sp = t % S, tt = t / S;
+                const int z = tt / tiles_per_z, r = tt - z * tiles_per_z;
                 const int m_tile = (r / n_tiles) * 2 + (int)rank, n_tile = r % n_tiles;
+                const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 int c_n = 0, c_h = 0, c_w = 0;
                 if (p.is_conv) {
                     int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tn = m_tile / (tiles_w * tiles_h);
@@ -389,7 +427,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                     c_h = th * p.tile_h * p.stride - p.pad_t;
                     c_n = tn * p.tile_n;                  // past the last image for a phantom tile: zero-filled
                 }
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + C::A_BYTES;
@@ -416,17 +454,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                const int sp = t % S;
+                const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
                     const uint64_t da = make_sw128_desc(a_addr), db = make_sw128_desc(a_addr + C::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
                     umma_commit_pair(empty_bar(stage), 3);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -440,7 +480,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-            const int z = t / tiles_per_z, r_ = t - z * tiles_per_z;
+            const int tt = t / S;
+            const int z = tt / tiles_per_z, r_ = tt - z * tiles_per_z;
             const int m_tile = (r_ / n_tiles) * 2 + (int)rank, n_tile = r_ % n_tiles;
             const int64_t m = (int64_t)m_tile * BM + row;
             mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -504,7 +545,7 @@ int launch_cps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
         DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CPS>::SMEM));
         configured = true;
     }
-    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1);
+    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
     int64_t slots = (int64_t)DM_NUM_SMS * CPS;
     unsigned grid = (unsigned)(tiles < slots ? tiles : slots);   // persistent: CPS CTAs per SM
     kern<<<grid, NTHREADS, Cfg<BN, CPS>::SMEM, st>>>(tmA, tmB, p);
@@ -515,9 +556,85 @@ int launch_cps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
 template <int BN, typename T>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
     if constexpr (BN <= 128) {
-        if (g_gemm_cps == 2) return launch_cps<BN, T, 2>(tmA, tmB, p, st);
+        // two co-resident CTAs only pay when there are more tiles than SMs; otherwise one CTA per SM with the full
+        // 192 KB ring (twice the loads in flight) hides the L2/HBM latency of the long-K, few-tile layers better
+        int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
+        if (g_gemm_cps == 2 && tiles > DM_NUM_SMS) return launch_cps<BN, T, 2>(tmA, tmB, p, st);
     }
     return launch_cps<BN, T, 1>(tmA, tmB, p, st);
+}
+
+// ---- split-K: few-tile, long-K layers (8x8 / 16x16 latents of a one-view batch) leave most SMs idle; S CTAs share a tile,
+// red.add fp32 partials into a zeroed workspace, and this kernel applies the epilogue and re-zeroes the workspace.
+float* g_ws = nullptr;
+size_t g_ws_floats = 0;
+int g_gemm_splitk = 1;
+constexpr size_t WS_FLOATS = 8u << 20;   // 32 MB: M*N <= 8 M elements
+
+bool ensure_ws(size_t floats, cudaStream_t st) {
+    if (floats > WS_FLOATS) return false;
+    if (g_ws) return true;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+    if (cudaMalloc(&g_ws, WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); g_ws = nullptr; return false; }
+    if (cudaMemset(g_ws, 0, WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); cudaFree(g_ws); g_ws = nullptr; return false; }
+    g_ws_floats = WS_FLOATS;
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmParams p) {
+    const int64_t n4 = p.N >> 2;
+    const int64_t total = (int64_t)(p.batch > 0 ? p.batch : 1) * p.M * n4;
+    const T* bias = (const T*)p.bias;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / n4; const int c = (int)(i - row * n4) * 4;
+        const int z = (int)(row / p.M); const int64_t m = row - (int64_t)z * p.M;
+        float4* w4 = reinterpret_cast<float4*>(p.ws + row * p.N + c);
+        float4 a = *w4;
+        *w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float f[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] += Cvt<T>::to_f(bias[c + j]);
+        }
+        if (p.rowvec) {
+            const T* rv = (const T*)p.rowvec + (m / p.rows_per_vec) * (int64_t)p.ld_rowvec;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] += Cvt<T>::to_f(rv[c + j]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+        } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+        }
+        if (p.residual) {
+            const T* res = (const T*)p.residual + (int64_t)z * p.res_batch_stride + m * (int64_t)p.ld_res;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] += Cvt<T>::to_f(res[c + j]);
+        }
+        const int64_t o = (int64_t)z * p.out_batch_stride + m * (int64_t)p.ldc + c;
+        if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float*>(p.out)[o + j] = f[j] * p.out_scale;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<T*>(p.out)[o + j] = Cvt<T>::from_f(f[j] * p.out_scale);
+        }
+    }
+}
+
+// split factor for a single-CTA launch of `tiles` output tiles with nk K-blocks (1 = no split)
+int pick_split(int64_t tiles, int nk, int64_t mn, int N, int act, bool out_ok, cudaStream_t st) {
+    if (!g_gemm_splitk || act == 3 || (N & 3) || !out_ok) return 1;
+    if (tiles * 2 > DM_NUM_SMS || nk < 32) return 1;
+    int s = (int)(DM_NUM_SMS / tiles);
+    if (s > nk / 8) s = nk / 8;
+    if (s > 16) s = 16;
+    if (s < 2 || !ensure_ws((size_t)mn, st)) return 1;
+    return s;
 }
 
 int g_gemm_pair = 1;  // 0 never, 1 where measured faster (use_pair), 2 wherever the shape allows (dm_tune_gemm 10/11/12)
@@ -536,22 +653,22 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = DM_NUM_SMS / 2; }
         max_clusters = n < DM_NUM_SMS / 2 ? n : DM_NUM_SMS / 2;
     }
-    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, 2 * BM) * (p.batch > 0 ? p.batch : 1);
+    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, 2 * BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
     unsigned clusters = (unsigned)(tiles < max_clusters ? tiles : max_clusters);
     kern<<<2 * clusters, NTHREADS, PairCfg<BN>::SMEM, st>>>(tmA, tmB, p);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
-struct TileChoice { int bn; bool pair; };
+struct TileChoice { int bn; bool pair; int split; };   // split: 0 = let dispatch decide (single-CTA path), >= 1 fixed
 
 int pick_bn(int64_t M, int N, int bn_hint);
 
 // Tile width and single-CTA vs CTA-pair kernel.  bn_hint: 0 auto; 64/128/256 single-CTA kernel of that width;
 // 1000 + {128,160,256} CTA-pair kernel of that width (experiments / tests).
-TileChoice choose_tile(int64_t M, int N, int bn_hint, int act) {
-    if (bn_hint >= 1000) return {bn_hint - 1000, true};
-    if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return {bn_hint, g_gemm_pair == 2 && bn_hint >= 128};
+TileChoice choose_tile(int64_t M, int N, int nk, int bn_hint, int act) {
+    if (bn_hint >= 1000) return {bn_hint - 1000, true, 1};
+    if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return {bn_hint, g_gemm_pair == 2 && bn_hint >= 128, g_gemm_pair == 2 && bn_hint >= 128 ? 1 : 0};
     if (g_gemm_pair) {
         // wide pair tiles: every SM reads A + B/2 per MMA and each weight tile is fetched once per 256 rows.  Measured
         // (scripts/sweep_tiles.py, profiles/r01_tile_sweep.md): 256-wide pairs beat the best single-CTA tile by 1.1-1.4x
@@ -560,26 +677,65 @@ TileChoice choose_tile(int64_t M, int N, int bn_hint, int act) {
         const int64_t mp = dm_ceil_div(M, 2 * BM);
         const int64_t tpcs = DM_NUM_SMS / 2;
         if (N >= 512 || N == 256) {
-            if (mp * dm_ceil_div(N, 256) >= tpcs) return {256, true};
+            const int64_t pt = mp * dm_ceil_div(N, 256);
+            if (pt >= tpcs) return {256, true, 1};
+            // few tiles: the layer is bound by L2->SMEM bytes (~12 TB/s chip-wide), which wide pair tiles cut 2-3x
+            // against 64-wide tiles; split-K spreads the K loop over the idle TPCs
+            // (the workspace pass costs ~10 us: only long K loops amortise it -- measured in scripts/exp_splitk.py)
+            if (g_gemm_splitk && act != 3 && (N & 3) == 0 && (nk >= 128 || (nk >= 64 && pt <= 8)) && (size_t)(M * N) <= WS_FLOATS) {
+                int64_t sp = tpcs / pt;
+                if (sp > nk / 8) sp = nk / 8;
+                if (sp > 16) sp = 16;
+                if (sp >= 2) return {256, true, (int)sp};
+            }
+            if (2 * pt >= tpcs) return {256, true, 1};
         } else if (N % 160 == 0 && act != 3) {
-            if (mp * (N / 160) >= 3 * tpcs) return {160, true};
+            if (mp * (N / 160) >= 3 * tpcs) return {160, true, 1};
         }
     }
-    return {pick_bn(M, N, 0), false};
+    return {pick_bn(M, N, 0), false, 0};
 }
 
-int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, bool pair, cudaStream_t st) {
-    if (pair) {
-        if (bf16) {
-            if (bn == 128) return launch_pair<128, __nv_bfloat16>(tmA, tmB, p, st);
-            if (bn == 160) return launch_pair<160, __nv_bfloat16>(tmA, tmB, p, st);
-            if (bn == 256) return launch_pair<256, __nv_bfloat16>(tmA, tmB, p, st);
-        } else {
-            if (bn == 128) return launch_pair<128, __half>(tmA, tmB, p, st);
-            if (bn == 160) return launch_pair<160, __half>(tmA, tmB, p, st);
-            if (bn == 256) return launch_pair<256, __half>(tmA, tmB, p, st);
-        }
+int dispatch_single(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st);
+
+int dispatch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st) {
+    if (bf16) {
+        if (bn == 128) return launch_pair<128, __nv_bfloat16>(tmA, tmB, p, st);
+        if (bn == 160) return launch_pair<160, __nv_bfloat16>(tmA, tmB, p, st);
+        if (bn == 256) return launch_pair<256, __nv_bfloat16>(tmA, tmB, p, st);
+    } else {
+        if (bn == 128) return launch_pair<128, __half>(tmA, tmB, p, st);
+        if (bn == 160) return launch_pair<160, __half>(tmA, tmB, p, st);
+        if (bn == 256) return launch_pair<256, __half>(tmA, tmB, p, st);
     }
+    dm_set_error("unsupported pair tile width %d", bn);
+    return DM_EUNSUPPORTED;
+}
+
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, const TileChoice& tc, int bf16, cudaStream_t st) {
+    GemmParams p = p_in;
+    const int64_t batch = p.batch > 0 ? p.batch : 1;
+    int split = 1;
+    if (tc.pair) {
+        if (tc.split > 1 && ensure_ws((size_t)(batch * p.M * p.N), st)) split = tc.split;
+    } else {
+        const int64_t tiles = dm_ceil_div(p.N, tc.bn) * dm_ceil_div(p.M, BM) * batch;
+        split = tc.split >= 1 ? 1 : pick_split(tiles, p.K / BK, batch * p.M * p.N, p.N, p.act, true, st);
+    }
+    p.split_k = split;
+    p.ws = split > 1 ? g_ws : nullptr;
+    int rc = tc.pair ? dispatch_pair(tmA, tmB, p, tc.bn, bf16, st) : dispatch_single(tmA, tmB, p, tc.bn, bf16, st);
+    if (rc || split <= 1) return rc;
+    const int64_t work = batch * p.M * (p.N >> 2);
+    int64_t blocks = dm_ceil_div(work, 256);
+    if (blocks > DM_NUM_SMS * 8) blocks = DM_NUM_SMS * 8;
+    if (bf16) splitk_finish_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else splitk_finish_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(p);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+int dispatch_single(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn, int bf16, cudaStream_t st) {
     if (bf16) {
         if (bn == 64) return launch<64, __nv_bfloat16>(tmA, tmB, p, st);
         if (bn == 128) return launch<128, __nv_bfloat16>(tmA, tmB, p, st);
@@ -625,6 +781,7 @@ void fill_epilogue(GemmParams& p, const dm_epilogue* e, int N) {
 
 extern "C" int dm_tune_gemm(int code) {
     if (code >= 10 && code <= 12) g_gemm_pair = code - 10;      // CTA-pair kernel: 10 off, 11 heuristic, 12 always
+    else if (code == 20 || code == 21) g_gemm_splitk = code - 20;  // split-K of few-tile long-K layers: off | on
     else g_gemm_cps = code == 1 ? 1 : 2;                        // single-CTA kernel: persistent CTAs per SM
     return DM_OK;
 }
@@ -642,8 +799,8 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
                    "GEGLU epilogue: N multiple of 64 (interleaved value/gate rows), 16-bit output of N/2 columns");
     }
     // batched GEMMs keep per-batch tiles; only the (possibly folded) batch-1 form pairs CTAs
-    TileChoice tc = (batch == 1) ? choose_tile(M, N, bn_hint, ep ? ep->act : 0)
-                                 : TileChoice{pick_bn((int64_t)M * batch, N, bn_hint >= 1000 ? 0 : bn_hint), false};
+    TileChoice tc = (batch == 1) ? choose_tile(M, N, K / BK, bn_hint, ep ? ep->act : 0)
+                                 : TileChoice{pick_bn((int64_t)M * batch, N, bn_hint >= 1000 ? 0 : bn_hint), false, 0};
     const int bn = tc.bn; const bool pair = tc.pair;
     if (ep && ep->act == 3) DM_REQUIRE(bn % 64 == 0, "GEGLU epilogue needs a tile width that is a multiple of 64");
     CUtensorMap tmA, tmB;
@@ -670,7 +827,7 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
     p.M = M; p.N = N; p.K = K; p.batch = batch; p.b_batched = (batch > 1) ? 1 : 0; p.is_conv = 0;
     p.out = C; p.ldc = (int)ldc; p.out_batch_stride = c_batch_stride;
     fill_epilogue(p, ep, N);
-    return dispatch(tmA, tmB, p, bn, bf16, pair, (cudaStream_t)stream);
+    return dispatch(tmA, tmB, p, tc, bf16, (cudaStream_t)stream);
 }
 
 extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const void* w, int Cout, int ksize,
@@ -685,7 +842,7 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     int tile_n = BM / (tile_w * tile_h);
     DM_REQUIRE(tile_w * tile_h * tile_n == BM && Wo % tile_w == 0 && Ho % tile_h == 0,
                "output extent must tile into 128-pixel boxes (power-of-two sizes)");
-    TileChoice tc = choose_tile((int64_t)n_img * Ho * Wo, Cout, bn_hint, ep ? ep->act : 0);
+    TileChoice tc = choose_tile((int64_t)n_img * Ho * Wo, Cout, ksize * ksize * Cin / BK, bn_hint, ep ? ep->act : 0);
     const int bn = tc.bn; const bool pair = tc.pair;
     CUtensorMap tmA, tmB;
     {
@@ -707,5 +864,5 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     p.Ho = Ho; p.Wo = Wo; p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
     p.out = y; p.ldc = (int)ldc; p.out_batch_stride = 0;
     fill_epilogue(p, ep, Cout);
-    return dispatch(tmA, tmB, p, bn, bf16, pair, (cudaStream_t)stream);
+    return dispatch(tmA, tmB, p, tc, bf16, (cudaStream_t)stream);
 }

@@ -32,7 +32,8 @@ int dm_version(void);
 /* scheduling knobs for experiments: "mc_refill", "mc_leaf_batch", "mc_skip_horizon" */
 int dm_tune(const char* key, int value);
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
-                                      * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible */
+                                      * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible;
+                                      * 20|21: split-K of few-tile, long-K layers off | on */
 /* number of kernels this library has launched in the process (bench.py's gpu_launches) */
 long long dm_launch_count(void);
 /* device sanity: returns 0 iff device `dev` is compute capability 10.x (sm_100a code present). */
