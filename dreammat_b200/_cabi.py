@@ -42,6 +42,7 @@ SIGNATURES = {
     "dm_launch_count": (C.c_longlong, []),
     "dm_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "dm_tune_gemm": (C.c_int, [C.c_int]),
+    "dm_tune_attention": (C.c_int, [C.c_int]),
     "dm_device_check": (C.c_int, [C.c_int]),
     "dm_hashgrid_layout": (I64, [P, P]),
     "dm_hashgrid_mlp_fwd": (C.c_int, [P, P, I64, P, P, P, P, P]),

@@ -54,11 +54,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+int g_attn_packed_exp = 0;   // dm_tune_attention(1): packed f16x2 exponentials (experiment)
+
 template <typename T> struct PK;
 template <> struct PK<__half> {
     static __device__ __forceinline__ uint32_t pack(float a, float b) {
         __half2 h = __floats2half2_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
+    }
+    // P row block = exp2(s*scale - max) for 64 keys, packed for the PV MMA, plus its row sum.
+    // The softmax warps are bound by the MUFU pipe (one ex2 per score: 4.5 T/s chip-wide, ncu profiles/r01b), so the
+    // fp16 path evaluates TWO exponentials per MUFU op (ex2.approx.f16x2 on the packed, already max-subtracted
+    // argument) -- the result is directly the fp16 pair the tensor core consumes.  The row sum is formed from those
+    // rounded values (two packed-add levels, then fp32), i.e. it normalises exactly what the MMA multiplies.
+    template <bool PACKED>
+    static __device__ __forceinline__ float exp_block(const uint32_t (&sv)[64], float scale, float neg_mx, uint32_t (&pk)[32]) {
+        if (!PACKED) {
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+                float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), scale, neg_mx));
+                float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), scale, neg_mx));
+                lsum += p0 + p1;
+                pk[c >> 1] = pack(p0, p1);
+            }
+            return lsum;
+        }
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+            __half2 x = __floats2half2_rn(fmaf(__uint_as_float(sv[c]), scale, neg_mx), fmaf(__uint_as_float(sv[c + 1]), scale, neg_mx));
+            uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+            pk[c >> 1] = yi;
+        }
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            __half2 a = __hadd2(*reinterpret_cast<const __half2*>(&pk[c]), *reinterpret_cast<const __half2*>(&pk[c + 1]));
+            __half2 b = __hadd2(*reinterpret_cast<const __half2*>(&pk[c + 2]), *reinterpret_cast<const __half2*>(&pk[c + 3]));
+            float2 f = __half22float2(__hadd2(a, b));
+            lsum += f.x + f.y;
+        }
+        return lsum;
     }
 };
 template <> struct PK<__nv_bfloat16> {
@@ -66,9 +103,22 @@ template <> struct PK<__nv_bfloat16> {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
     }
+    // bf16 keeps the fp32 exponentials (8 mantissa bits are too few for packed sums)
+    template <bool PACKED>
+    static __device__ __forceinline__ float exp_block(const uint32_t (&sv)[64], float scale, float neg_mx, uint32_t (&pk)[32]) {
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), scale, neg_mx));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), scale, neg_mx));
+            lsum += p0 + p1;
+            pk[c >> 1] = pack(p0, p1);
+        }
+        return lsum;
+    }
 };
 
-template <typename T>
+template <typename T, int MODE>   // MODE 0: fp32 exponentials, rescale every block; 1: packed f16x2 exp + lazy rescale; 2: fp32 exp + lazy rescale
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
@@ -191,19 +241,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
                     mraw = fmaxf(mraw, s);
                 }
             }
-            const float mx = fmaxf(m_run, mraw * p.scale_log2e);   // running max in the scaled (log2) domain
-            const float alpha = fast_exp2(m_run - mx);             // m_run = -inf on the first block -> 0
-            const float neg_mx = -mx;
-            float lsum = 0.f;
+            // Lazy rescaling: the reference max only moves when some row's new maximum exceeds it by more than 2^8 (P then
+            // stays <= 256, exact in fp16/fp32); otherwise alpha == 1 and the 64-register rescale is skipped.  The final
+            // O / l division cancels the stale reference exactly.
+            const float mx_new = fmaxf(m_run, mraw * p.scale_log2e);   // running max in the scaled (log2) domain
+            constexpr bool PACKED = (MODE == 1);
+            constexpr bool LAZY = (MODE != 0);
+            const bool need = !LAZY || !(mx_new - m_run <= 8.0f);     // also true on the first block (m_run = -inf)
+            const bool any_need = !LAZY || __any_sync(0xffffffffu, need);
+            const float mx = need ? mx_new : m_run;
             uint32_t pk[32];
-#pragma unroll
-            for (int c = 0; c < AK; c += 2) {
-                // one FFMA + one MUFU.EX2 per element: exp2(s * scale*log2e - max)
-                float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2e, neg_mx));
-                float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2e, neg_mx));
-                lsum += p0 + p1;
-                pk[c >> 1] = PK<T>::pack(p0, p1);
-            }
+            const float lsum = PK<T>::template exp_block<PACKED>(sv, p.scale_log2e, -mx, pk);
             // previous block's O_j (computed against the previous max) joins the accumulator before the rescale
             if (j > 0) {
                 mbar_wait(o_full, (uint32_t)((j - 1) & 1));
@@ -217,10 +265,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
                     for (int c = 0; c < 32; ++c) acc[32 * hh + c] += __uint_as_float(t0[c]);
                 }
             }
+            if (any_need) {
+                const float alpha = fast_exp2(m_run - mx);             // m_run = -inf on the first block -> 0
 #pragma unroll
-            for (int c = 0; c < HD; ++c) acc[c] *= alpha;
-            l_run = l_run * alpha + lsum;
-            m_run = mx;
+                for (int c = 0; c < HD; ++c) acc[c] *= alpha;
+                l_run = l_run * alpha + lsum;
+                m_run = mx;
+            } else {
+                l_run += lsum;
+            }
             // P_j -> shared memory, 128B-swizzled K-major tile (16-byte chunk index XOR row%8)
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -290,6 +343,8 @@ int encode3(CUtensorMap* m, int bf16, const void* base, uint64_t cols, uint64_t 
 
 }  // namespace
 
+extern "C" int dm_tune_attention(int mode) { g_attn_packed_exp = (mode == 1 || mode == 2) ? mode : 0; return DM_OK; }
+
 extern "C" int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, const void* v,
                             int64_t ldkv, int64_t kv_batch_stride, void* out, int64_t ldo, int64_t out_batch_stride,
                             int batch, int heads, int Nq, int Nk, int head_dim, float scale, void* stream) {
@@ -307,11 +362,18 @@ extern "C" int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batc
     dim3 grid((unsigned)dm_ceil_div(Nq, AQ), (unsigned)heads, (unsigned)batch);
     static bool cfg_h = false, cfg_b = false;
     if (bf16) {
-        if (!cfg_b) { DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); cfg_b = true; }
-        attention_kernel<__nv_bfloat16><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        if (!cfg_b) { DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); cfg_b = true; }
+        attention_kernel<__nv_bfloat16, 0><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
     } else {
-        if (!cfg_h) { DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); cfg_h = true; }
-        attention_kernel<__half><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        if (!cfg_h) {
+            DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+            DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+            DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+            cfg_h = true;
+        }
+        if (g_attn_packed_exp == 1) attention_kernel<__half, 1><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        else if (g_attn_packed_exp == 2) attention_kernel<__half, 2><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        else attention_kernel<__half, 0><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
     }
     DM_CHECK_LAUNCH();
     return DM_OK;

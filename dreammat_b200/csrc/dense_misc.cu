@@ -286,20 +286,48 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, int64_t M, int C,
                                                         const T* __restrict__ gamma, const T* __restrict__ beta,
                                                         float eps, T* __restrict__ y) {
+    // warp per row, 16-byte vectors (C % 8 == 0, C <= 1280 -> at most 5 vectors per lane kept in registers);
+    // two-pass mean / centred variance on the register copy
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, nv = C >> 3;
     const T* xr = x + row * C;
-    float vals[40];  // C <= 1280 -> 40 per lane
-    int cnt = 0; float s = 0.f;
-    for (int c = lane; c < C; c += 32) { float v = H<T>::f(xr[c]); vals[cnt++] = v; s += v; }
+    float vals[40];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nv) {
+            uint4 u = *reinterpret_cast<const uint4*>(xr + 8 * v);
+            const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float f = H<T>::f(h[j]); vals[8 * k + j] = f; s += f; }
+        }
+    }
     s = warp_sum(s);
-    float mean = s / (float)C, ss = 0.f;
-    for (int k = 0; k < cnt; ++k) { float d = vals[k] - mean; ss += d * d; }
+    const float mean = s / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (lane + 32 * k < nv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float d = vals[8 * k + j] - mean; ss += d * d; }
+        }
+    }
     ss = warp_sum(ss);
-    float rstd = rsqrtf(ss / (float)C + eps);
-    cnt = 0;
-    for (int c = lane; c < C; c += 32) y[row * C + c] = H<T>::t((vals[cnt++] - mean) * rstd * H<T>::f(gamma[c]) + H<T>::f(beta[c]));
+    const float rstd = rsqrtf(ss / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nv) {
+            uint4 ug = *reinterpret_cast<const uint4*>(gamma + 8 * v), ub = *reinterpret_cast<const uint4*>(beta + 8 * v);
+            const T* hg = reinterpret_cast<const T*>(&ug); const T* hb = reinterpret_cast<const T*>(&ub);
+            uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) oh[j] = H<T>::t((vals[8 * k + j] - mean) * rstd * H<T>::f(hg[j]) + H<T>::f(hb[j]));
+            *reinterpret_cast<uint4*>(y + row * C + 8 * v) = o;
+        }
+    }
 }
 
 // GEGLU: out[m, j] = h[m, j] * gelu(h[m, D + j])   (diffusers GEGLU: hidden, gate = chunk(2); hidden * gelu(gate))
@@ -372,13 +400,27 @@ __global__ void __launch_bounds__(256) axpby2d_kernel(const T* __restrict__ s1, 
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ x, int R, int C, int64_t ldx,
                                                         int64_t bsx, T* __restrict__ y, int64_t ldy, int64_t bsy) {
-    __shared__ T tile[32][33];
+    // 64 x 64 tile of 16-bit elements moved as 32-bit pairs on both sides (128-byte warp requests): the load packs two
+    // neighbouring columns, the store two neighbouring rows of the input.  Even R, C, ld (checked on the host).
+    __shared__ uint32_t tile[64][33];     // [row][column pair]
     const T* xb = x + (int64_t)blockIdx.z * bsx; T* yb = y + (int64_t)blockIdx.z * bsy;
-    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int j = ty; j < 32; j += 8) { int r = r0 + j, c = c0 + tx; if (r < R && c < C) tile[j][tx] = xb[(int64_t)r * ldx + c]; }
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 64; j += 8) {
+        int r = r0 + j, c = c0 + 2 * tx;
+        uint32_t v = 0;
+        if (r < R && c < C) v = *reinterpret_cast<const uint32_t*>(xb + (int64_t)r * ldx + c);
+        tile[j][tx] = v;
+    }
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) { int c = c0 + j, r = r0 + tx; if (r < R && c < C) yb[(int64_t)c * ldy + r] = tile[tx][j]; }
+    for (int j = ty; j < 64; j += 8) {       // output row c0 + j holds input column c0 + j; this thread writes rows r0+2tx, +1
+        int c = c0 + j, r = r0 + 2 * tx;
+        if (c < C && r < R) {
+            uint32_t lo = tile[2 * tx][j >> 1], hi = tile[2 * tx + 1][j >> 1];
+            uint32_t a = (j & 1) ? (lo >> 16) : (lo & 0xffffu), bq = (j & 1) ? (hi >> 16) : (hi & 0xffffu);
+            *reinterpret_cast<uint32_t*>(yb + (int64_t)c * ldy + r) = a | (bq << 16);
+        }
+    }
 }
 
 // row softmax: y = softmax(scale * x) over `cols`; one block per row
@@ -427,10 +469,15 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) pad_convert_kernel(const float* __restrict__ x, int64_t rows, int cin, int cpad,
                                                           float scale, float shift, T* __restrict__ y) {
-    int64_t n = rows * cpad;
+    // one 16-byte store (8 channels) per thread; cpad % 8 == 0
+    const int vpr = cpad >> 3;
+    const int64_t n = rows * vpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / cpad; int c = (int)(i - r * cpad);
-        y[i] = H<T>::t(c < cin ? x[r * cin + c] * scale + shift : 0.f);
+        const int64_t r = i / vpr; const int c0 = (int)(i - r * vpr) * 8;
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) oh[k] = H<T>::t((c0 + k < cin) ? fmaf(x[r * cin + c0 + k], scale, shift) : 0.f);
+        *reinterpret_cast<uint4*>(y + r * cpad + c0) = o;
     }
 }
 // T [rows, ld] (first cout channels) -> fp32 [rows, cout] * scale
@@ -585,7 +632,7 @@ extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_i
 extern "C" int dm_layernorm(int bf16, const void* x, int64_t M, int C, const void* gamma, const void* beta, float eps,
                             void* y, void* stream) {
     DM_REQUIRE(x && gamma && beta && y, "null pointer");
-    DM_REQUIRE(C <= 1280, "C <= 1280");
+    DM_REQUIRE(C <= 1280 && C % 8 == 0, "C <= 1280, multiple of 8");
     if (M == 0) return DM_OK;
     DM_DISPATCH_T(bf16, layernorm_kernel<T><<<(unsigned)dm_ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, (const T*)gamma,
                                                                                                         (const T*)beta, eps, (T*)y));
@@ -622,7 +669,9 @@ extern "C" int dm_axpby2d(int bf16, const void* s1, int64_t ld1, float a, const 
 extern "C" int dm_transpose(int bf16, const void* x, int batch, int R, int C, int64_t ldx, int64_t bsx, void* y,
                             int64_t ldy, int64_t bsy, void* stream) {
     DM_REQUIRE(x && y, "null pointer");
-    dim3 grid((unsigned)dm_ceil_div(C, 32), (unsigned)dm_ceil_div(R, 32), (unsigned)batch);
+    DM_REQUIRE(((R | C) & 1) == 0 && ((ldx | ldy | bsx | bsy) & 1) == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 3) == 0,
+               "transpose moves 32-bit pairs: even extents / strides, 4-byte aligned bases");
+    dim3 grid((unsigned)dm_ceil_div(C, 64), (unsigned)dm_ceil_div(R, 64), (unsigned)batch);
     DM_DISPATCH_T(bf16, transpose_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, R, C, ldx, bsx, (T*)y, ldy, bsy));
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -648,8 +697,8 @@ extern "C" int dm_softmax_bwd(int bf16, const void* P, const void* dP, int64_t r
 
 extern "C" int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, int cpad, float scale, float shift,
                               void* y, void* stream) {
-    DM_REQUIRE(x && y && cpad >= cin, "bad args");
-    DM_DISPATCH_T(bf16, pad_convert_kernel<T><<<grid_for(rows * cpad), 256, 0, (cudaStream_t)stream>>>(x, rows, cin, cpad, scale, shift, (T*)y));
+    DM_REQUIRE(x && y && cpad >= cin && cpad % 8 == 0, "bad args (cpad must be a multiple of 8)");
+    DM_DISPATCH_T(bf16, pad_convert_kernel<T><<<grid_for(rows * (cpad / 8)), 256, 0, (cudaStream_t)stream>>>(x, rows, cin, cpad, scale, shift, (T*)y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

@@ -261,7 +261,38 @@ __global__ void __launch_bounds__(NTHREADS) hashgrid_bwd_kernel(LevelMeta m, con
                 for (int kk = 0; kk < 8; ++kk) acc[kk] = fmaf(dh, s_w1[h][lg * 8 + kk], acc[kk]);
             }
             // levels [4*lg, 4*lg+4) own encoding columns [8*lg, 8*lg+8): scatter directly
-            if (valid) {
+            if (lg < 2) {
+                // Coarse levels (0-7): the 32 consecutive surface points of a warp fall into a handful of cells, so
+                // plain atomics serialise on the same few addresses (level 0 has 4 913 vertices for ~10^5 points).
+                // Runs of equal vertex index along the warp are summed with a segmented shuffle reduction and only the
+                // head lane of each run issues the atomic.  (lg is warp-uniform: a warp is 32 points of one level group.)
+                const int lane = tid & 31;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int l = lg * 4 + j;
+                    if (l < m.n_levels) {               // warp-uniform
+                        Corner c;
+                        if (valid) level_corners(m, l, x, y, z, c);
+                        float g0 = acc[2 * j], g1 = acc[2 * j + 1];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            uint32_t idx = valid ? c.idx[k] : 0xffffffffu;
+                            float v0 = valid ? c.w[k] * g0 : 0.f, v1 = valid ? c.w[k] * g1 : 0.f;
+                            uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+                            const bool head = (lane == 0) || (idx != prev);
+                            const unsigned heads = __ballot_sync(0xffffffffu, head);
+                            const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));   // heads at lane+1, lane+2, ...
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                float o0 = __shfl_down_sync(0xffffffffu, v0, d), o1 = __shfl_down_sync(0xffffffffu, v1, d);
+                                // lane + d belongs to this lane's run iff no head lies in (lane, lane + d]
+                                if (lane + d < 32 && (after & ((1u << d) - 1u)) == 0u) { v0 += o0; v1 += o1; }
+                            }
+                            if (head && idx != 0xffffffffu) atomicAdd(dgrid + idx, make_float2(v0, v1));
+                        }
+                    }
+                }
+            } else if (valid) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     int l = lg * 4 + j;

@@ -31,6 +31,7 @@ const char* dm_last_error(void);
 int dm_version(void);
 /* scheduling knobs for experiments: "mc_refill", "mc_leaf_batch", "mc_skip_horizon" */
 int dm_tune(const char* key, int value);
+int dm_tune_attention(int packed_exp); /* experiment: ex2.approx.f16x2 softmax exponentials (fp16 only) */
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
                                       * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible;
                                       * 20|21: split-K of few-tile, long-K layers off | on */
