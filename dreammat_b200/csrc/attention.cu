@@ -70,15 +70,18 @@ template <> struct PK<__half> {
     template <bool PACKED>
     static __device__ __forceinline__ float exp_block(const uint32_t (&sv)[64], float scale, float neg_mx, uint32_t (&pk)[32]) {
         if (!PACKED) {
-            float lsum = 0.f;
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;      // independent partial row sums (no 64-long FADD chain)
 #pragma unroll
-            for (int c = 0; c < 64; c += 2) {
+            for (int c = 0; c < 64; c += 4) {
                 float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), scale, neg_mx));
                 float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), scale, neg_mx));
-                lsum += p0 + p1;
+                float p2 = fast_exp2(fmaf(__uint_as_float(sv[c + 2]), scale, neg_mx));
+                float p3 = fast_exp2(fmaf(__uint_as_float(sv[c + 3]), scale, neg_mx));
+                l0 += p0; l1 += p1; l2 += p2; l3 += p3;
                 pk[c >> 1] = pack(p0, p1);
+                pk[(c >> 1) + 1] = pack(p2, p3);
             }
-            return lsum;
+            return (l0 + l1) + (l2 + l3);
         }
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
@@ -106,15 +109,18 @@ template <> struct PK<__nv_bfloat16> {
     // bf16 keeps the fp32 exponentials (8 mantissa bits are too few for packed sums)
     template <bool PACKED>
     static __device__ __forceinline__ float exp_block(const uint32_t (&sv)[64], float scale, float neg_mx, uint32_t (&pk)[32]) {
-        float lsum = 0.f;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
+        for (int c = 0; c < 64; c += 4) {
             float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), scale, neg_mx));
             float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), scale, neg_mx));
-            lsum += p0 + p1;
+            float p2 = fast_exp2(fmaf(__uint_as_float(sv[c + 2]), scale, neg_mx));
+            float p3 = fast_exp2(fmaf(__uint_as_float(sv[c + 3]), scale, neg_mx));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
             pk[c >> 1] = pack(p0, p1);
+            pk[(c >> 1) + 1] = pack(p2, p3);
         }
-        return lsum;
+        return (l0 + l1) + (l2 + l3);
     }
 };
 
@@ -231,8 +237,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
             const int kvalid = p.Nk - j * AK;  // keys of this block that exist
             float mraw = -INFINITY;
             if (kvalid >= AK) {
+                // four independent running maxima: a single 64-long dependent FMNMX chain costs ~250 cycles of latency per block
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < AK; ++c) mraw = fmaxf(mraw, __uint_as_float(sv[c]));
+                for (int c = 0; c < AK; c += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(sv[c])); m1 = fmaxf(m1, __uint_as_float(sv[c + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(sv[c + 2])); m3 = fmaxf(m3, __uint_as_float(sv[c + 3]));
+                }
+                mraw = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             } else {            // ragged last block (cross-attention over 77 tokens): mask the missing keys
 #pragma unroll
                 for (int c = 0; c < AK; ++c) {
