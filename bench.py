@@ -122,6 +122,7 @@ def run_ours(args):
     Vl = V // world
     sysm, cams = build_system(device, args.res, args.faces, (args.env_h, args.env_w), 0, dtype)
     sysm.world_size, sysm.rank = world, rank
+    sysm.balance_pixels = not args.no_balance
     if not args.no_graphs:
         sysm.guidance.enable_graphs(Vl, args.res, args.res)     # dense section as three captured CUDA graphs
     res = args.res
@@ -148,7 +149,8 @@ def run_ours(args):
         tot_pn = int(sum(pn[int(v)] for v in view_id))
         mine = slice(rank * Vl, (rank + 1) * Vl)
         vid, eid = view_id[mine], env_id[mine]
-        b = {"view_id": vid, "env_id": eid, "height": res, "width": res, "rays_o": [None] * Vl, "rays_d": [None] * Vl}
+        b = {"view_id": vid, "env_id": eid, "height": res, "width": res, "rays_o": [None] * Vl, "rays_d": [None] * Vl,
+             "global_view_id": view_id, "global_env_id": env_id}   # lets the step balance the shading over the ranks
         for k in ("mvp_mtx", "w2c", "elevation", "azimuth", "camera_distances"):
             b[k] = torch.cat([cam_dev[int(v)][k] for v in vid], 0)
         sel = [(int(v) * 5 + int(e)) % POOL for v, e in zip(vid, eid)]
@@ -212,7 +214,7 @@ def run_ours(args):
            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16",
            "data": "synthetic (procedural %d-face mesh, synthetic HDR env maps and condition maps, seeded random SD-2.1-base/ControlNet/VAE weights)" % args.faces,
            "config": {"workload": "north-star: %dx%d, %d-view batch (%d/GPU), 200+128 MC rays/px, 5 env maps, 128 fixed views" % (res, res, V, Vl),
-                      "views": V, "resolution": res, "parallelism": "dp%d (views sharded, 1 all-reduce of 50.4 MB grads)" % world,
+                      "views": V, "resolution": res, "parallelism": "dp%d (views sharded; shading pixels balanced over ranks by 2 small all-to-alls; 1 all-reduce of 50.4 MB grads)" % world,
                       "l2": "working set (2.5 GB weights + activations) exceeds the 126 MB L2 every step"},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": 1000.0 / ms_e2e, "unit": "it/s", "h2d_bytes_per_step": int(Vl * res * res * 22 * 4),
@@ -368,6 +370,7 @@ def main():
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="multi-GPU: every rank shades only its own views")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner, nvcc/ninja chatter)
     # are sent to stderr for the whole run and the result line is written to the saved descriptor.

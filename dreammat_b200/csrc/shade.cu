@@ -118,6 +118,25 @@ struct PixState {
     float a, NoV, rd, rs, g1v, g1d;
 };
 
+// specular sample direction about the reflection vector (value and d/da), dreammat_material.py:575-596
+__device__ __forceinline__ D3 spec_direction(const PixState& px, float phi0, float ue) {
+    float phi = phi0 + px.rs;
+    phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    const Dual aD = mkd(px.a, 1.0f);
+    // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
+    Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
+    Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
+    Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
+    Dual cx = st * cs, cy = st * sn;
+    D3 d;
+    d.x = cx * px.xs[0] + cy * px.ys[0] + ct * px.r[0];
+    d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
+    d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
+    return d;
+}
+
 __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
@@ -126,6 +145,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
     const int nd = P.cfg.n_diffuse, ns = P.cfg.n_specular, S = nd + ns;
     float* s_td = s_tab;
     float* s_ts = s_tab + 3 * nd;
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_tab + 3 * nd + 2 * ns);   // [MC_WARPS][S] compacted sample ids
     for (int i = threadIdx.x; i < nd; i += blockDim.x) {
         float ua = P.tab_d[2 * i], ue = P.tab_d[2 * i + 1];
         s_td[3 * i] = ua * PI_F * 2.0f;            // az = az * pi * 2 (:563)
@@ -173,17 +193,39 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
         float Ud[3] = {0, 0, 0}, Vd[3] = {0, 0, 0};    // d/da of the above with fh held fixed
         float Wd[3] = {0, 0, 0};                       // sum L*w*dfh/da
 
-        // ---- sample loop: the two sample families are visited in separate warp-aligned segments (lane = sample slot).
-        // Measured alternatives (profiles/r01_shade_experiments.md): persistent per-lane ray state machines with warp refill
-        // and batched leaf tests were 10-60 % SLOWER than this lock-step loop once the per-step cost was cut
-        // (precomputed triangle edges, pre-widened slabs, occlusion before BRDF math).
-        const int it_d = (nd + 31) >> 5, it_s = (ns + 31) >> 5;
-        for (int it = 0; it < it_d + it_s; ++it) {
-            const bool spec = it >= it_d;
-            const int slot = (spec ? (it - it_d) : it) * 32 + lane;
-            if (slot >= (spec ? ns : nd)) continue;
-            int s = spec ? nd + slot : slot;
-            if (P.perm) s = P.perm[s];
+        // ---- work list.  Specular samples whose direction falls below the horizon have NoL = 0 -> G = 0 -> weight and
+        // d(weight)/da exactly 0; unless the aux light maps are requested their radiance is never used, so they are not
+        // traced.  Instead of idling their lanes, the surviving sample ids are compacted (ballot + prefix count) behind the
+        // diffuse ids, so every pass of the loop below runs with 32 live rays and there are fewer passes.
+        uint16_t* list = s_list + warp * S;
+        const bool compact = P.skip_horizon && !P.spec_light && !P.hit_bits;
+        int count;
+        if (compact) {
+            for (int i = lane; i < nd; i += 32) list[i] = (uint16_t)i;
+            count = nd;
+            for (int j0 = 0; j0 < ns; j0 += 32) {
+                const int j = j0 + lane;
+                bool act = false;
+                if (j < ns) {
+                    D3 d = spec_direction(px, s_ts[2 * j], s_ts[2 * j + 1]);
+                    act = (d.x.v * px.n[0] + d.y.v * px.n[1] + d.z.v * px.n[2]) > 0.0f;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, act);
+                if (act) list[count + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(nd + j);
+                count += __popc(bal);
+            }
+        } else {
+            for (int i = lane; i < S; i += 32) list[i] = (uint16_t)(P.perm ? P.perm[i] : i);
+            count = S;
+        }
+        __syncwarp();
+        // ---- sample loop (lane = slot of the work list).  Samples are visited in table order: Fibonacci points sorted by
+        // elevation, so the 32 rays of a pass leave the surface at the same angle and have similar traversal lengths
+        // (direction-coherent orders measured 10 % slower, profiles/r01_shade_experiments.md).
+        for (int base = 0; base < count; base += 32) {
+            if (base + lane >= count) continue;
+            const int s = list[base + lane];
+            const bool spec = s >= nd;
             // ---- sample direction (value and d/da), :554-596
             D3 d;
             if (!spec) {
@@ -197,20 +239,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
                 d.z = mkd(cx * px.xd[2] + cy * px.yd[2] + cz * px.n[2]);
             } else {
                 const int j = s - nd;
-                float ue = s_ts[2 * j + 1];
-                float phi = s_ts[2 * j] + px.rs;
-                phi = phi - floorf(phi / TWO_PI_F) * TWO_PI_F;
-                float sn, cs;
-                sincosf(phi, &sn, &cs);
-                const Dual aD = mkd(px.a, 1.0f);
-                // cos_theta = sqrt((1-el+1e-6)/(1+(a^2-1) el+1e-6)+1e-6) (:585)
-                Dual den = (aD * aD - 1.0f) * ue + (1.0f + 1e-6f);
-                Dual ct = dsqrt(mkd(1.0f - ue + 1e-6f) / den + 1e-6f);
-                Dual st = dsqrt(1.0f - ct * ct + 1e-6f);
-                Dual cx = st * cs, cy = st * sn;
-                d.x = cx * px.xs[0] + cy * px.ys[0] + ct * px.r[0];
-                d.y = cx * px.xs[1] + cy * px.ys[1] + ct * px.r[1];
-                d.z = cx * px.xs[2] + cy * px.ys[2] + ct * px.r[2];
+                d = spec_direction(px, s_ts[2 * j], s_ts[2 * j + 1]);
             }
             const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
             // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless the
@@ -534,7 +563,14 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
     P.skip_horizon = g_mc_skip_horizon;
-    size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float);
+    // direction tables + one compacted sample-id list per warp
+    size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float) +
+                  (size_t)MC_WARPS * (cfg->n_diffuse + cfg->n_specular) * sizeof(uint16_t);
+    static size_t smem_configured = 48 * 1024;
+    if (smem > smem_configured) {
+        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_configured = smem;
+    }
     shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
     return DM_OK;

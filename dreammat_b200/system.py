@@ -324,6 +324,7 @@ class DreamMat:
         self.v = torch.zeros_like(geometry.params)
         self.global_step = 0
         self.world_size, self.rank = 1, 0
+        self.balance_pixels = True     # multi-GPU: shade equal pixel intervals of the global batch (parallel.pixel_partition)
         # dreammat_guidance.py:507-513: renders that are not 512x512 are resized (bilinear) to 512x512 before the VAE
         self.resize_to_vae = True
 
@@ -389,7 +390,24 @@ class DreamMat:
         gbs = [ren.gbuffer(batch["rays_o"][b:b + 1], batch["rays_d"][b:b + 1], batch["mvp_mtx"][b:b + 1],
                            batch["w2c"][b:b + 1], int(batch["view_id"][b])) for b in range(B)]
         total_pn = total_pn_global or sum(g["pn"] for g in gbs)
-        self._last_pn = sum(g["pn"] for g in gbs)
+        own_px = sum(g["pn"] for g in gbs)
+        # ---- who shades what.  Default: this rank's own views.  With the global batch known (`global_view_id` /
+        # `global_env_id`, every view in the G-buffer cache) the covered pixels of ALL views are cut into equal intervals
+        # (parallel.pixel_partition) so the ray-tracing load does not depend on which views a rank drew.
+        balanced = (self.world_size > 1 and self.balance_pixels and rng is None and "global_view_id" in batch and
+                    all(int(v) in ren._cache for v in batch["global_view_id"]))
+        if balanced:
+            from .parallel import exchange_rows, pixel_partition
+            gvid = [int(v) for v in batch["global_view_id"]]
+            geid = [int(e) for e in batch["global_env_id"]]
+            segments, counts = pixel_partition([ren._cache[v]["pn"] for v in gvid], self.world_size)
+            my_segs = [(ren._cache[gvid[g]], geid[g], a, bb, g) for (g, a, bb) in segments[self.rank]]
+            send_counts = counts[self.rank]
+            recv_counts = [counts[r][self.rank] for r in range(self.world_size)]
+        else:
+            my_segs = [(g, int(batch["env_id"][b]), 0, g["pn"], b) for b, g in enumerate(gbs)]
+        n_sh = sum(bb - a for (_, _, a, bb, _) in my_segs)
+        self._last_pn = n_sh
         g_ = getattr(guid, "graphs", None)
         resize = self.resize_to_vae and (H != 512 or W != 512)
         use_graphs = g_ is not None and g_.B == B and rng is None
@@ -397,30 +415,41 @@ class DreamMat:
         raw = torch.empty(B, H * W, 3, device=dev)            # canvas before the antialias blend
         check(lib().dm_fill(ptr(raw), raw.numel(), 1.0, st), "dm_fill")
         reg_sums = torch.zeros(2, device=dev)
+        color_sh = torch.empty(max(n_sh, 1), 3, device=dev)   # colours of the pixels this rank shades, segment order
+        jac_sh = torch.empty(max(n_sh, 1), 9, device=dev)
         saved = []
-        for b, g in enumerate(gbs):
-            n = g["pn"]
+        o = 0
+        for (ge, env_id, a, bb, gi) in my_segs:
+            n = bb - a
+            pts, nrm, vd = ge["pts"][a:bb], ge["nrm"][a:bb], ge["vd"][a:bb]
             if rng is not None:   # explicit randomness for parity tests
-                ang, eps, rd, rs = (rng[k][b].to(dev).reshape(-1).contiguous() for k in ("rand_ang", "normal_eps", "rand_d", "rand_s"))
+                ang, eps, rd, rs = (rng[k][gi].to(dev).reshape(-1).contiguous() for k in ("rand_ang", "normal_eps", "rand_d", "rand_s"))
             else:
                 ang, eps = torch.rand(n, device=dev), torch.randn(n, device=dev) * ren.change_eps
                 rd, rs = torch.rand(n, device=dev), torch.rand(n, device=dev)
-            pj = R.jitter_positions(g["pts"], g["nrm"], ang, eps)
+            pj = R.jitter_positions(pts, nrm, ang, eps)
             f = torch.empty(n, 5, device=dev); fj = torch.empty(n, 5, device=dev)
-            check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(g["pts"]), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(f), st), "hashgrid fwd")
+            check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(pts), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(f), st), "hashgrid fwd")
             check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(pj), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(fj), st), "hashgrid fwd")
-            color = torch.empty(n, 3, device=dev); jac = torch.empty(n, 9, device=dev)
-            env = mat.light[int(batch["env_id"][b])]
+            env = mat.light[env_id]
+            color, jac = color_sh[o:o + n], jac_sh[o:o + n]
             check(lib().dm_shade_mc_fwd(C.byref(mat.mc_cfg), ren.ray_tracer.h, ptr(env), env.shape[0], env.shape[1],
-                                        ptr(mat.tab_d), ptr(mat.tab_s), ptr(g["pts"]), ptr(g["nrm"]), ptr(g["vd"]), ptr(f),
+                                        ptr(mat.tab_d), ptr(mat.tab_s), ptr(pts), ptr(nrm), ptr(vd), ptr(f),
                                         ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
                                         None, ptr(mat.perm), st), "dm_shade_mc_fwd")
-            check(lib().dm_scatter_canvas(ptr(color), ptr(g["pix"]), n, 3, ptr(raw[b]), st), "dm_scatter_canvas")
+            saved.append((pts, pj, f, fj, jac, n, o))
+            o += n
+        # colours travel to the ranks that own the views (one all-to-all); without balancing they are already home
+        color_own = exchange_rows(color_sh[:n_sh], send_counts, recv_counts, self.world_size) if balanced else color_sh
+        o = 0
+        for b, g in enumerate(gbs):
+            n = g["pn"]
+            check(lib().dm_scatter_canvas(ptr(color_own[o:o + n]), ptr(g["pix"]), n, 3, ptr(raw[b]), st), "dm_scatter_canvas")
             aa = g.get("aa")
             k_aa = int(aa[0].shape[0]) if aa is not None else 0
             check(lib().dm_antialias_fwd(ptr(raw[b]), ptr(aa[0]) if k_aa else None, ptr(aa[1]) if k_aa else None,
                                          ptr(aa[2]) if k_aa else None, k_aa, H * W, 3, ptr(canvas[b]), st), "dm_antialias_fwd")
-            saved.append((g, pj, f, fj, jac))
+            o += n
         comp_rgb = canvas.view(B, H, W, 3)
         vae_in = comp_rgb
         if resize:
@@ -455,19 +484,24 @@ class DreamMat:
         gout = {"grad_norm": sums[1].sqrt()}
         # backward into the hash grid / MLP
         geo.grads.zero_()
-        for b, (g, pj, f, fj, jac) in enumerate(saved):
+        dcolor_own = torch.empty(max(own_px, 1), 3, device=dev)
+        o = 0
+        for b, g in enumerate(gbs):
             n = g["pn"]
-            dcolor = torch.empty(n, 3, device=dev)
             aa = g.get("aa")
             k_aa = int(aa[0].shape[0]) if aa is not None else 0
             draw = torch.empty(H * W, 3, device=dev)
             check(lib().dm_antialias_bwd(ptr(dcanvas[b]), ptr(aa[0]) if k_aa else None, ptr(aa[1]) if k_aa else None,
                                          ptr(aa[2]) if k_aa else None, k_aa, H * W, 3, ptr(draw), st), "dm_antialias_bwd")
-            check(lib().dm_gather_canvas_grad(ptr(draw), ptr(g["pix"]), n, 3, ptr(dcolor), st), "gather")
+            check(lib().dm_gather_canvas_grad(ptr(draw), ptr(g["pix"]), n, 3, ptr(dcolor_own[o:o + n]), st), "gather")
+            o += n
+        # d loss / d colour back to the shading ranks (the forward all-to-all, transposed)
+        dcolor_sh = exchange_rows(dcolor_own[:own_px], recv_counts, send_counts, self.world_size) if balanced else dcolor_own
+        for (pts, pj, f, fj, jac, n, o) in saved:
             df = torch.empty(n, 5, device=dev); dfj = torch.empty(n, 5, device=dev)
-            check(lib().dm_shade_bwd(C.byref(mat.mc_cfg), ptr(f), ptr(fj), ptr(dcolor), ptr(jac), lam_reg * 0.25 / total_pn,
+            check(lib().dm_shade_bwd(C.byref(mat.mc_cfg), ptr(f), ptr(fj), ptr(dcolor_sh[o:o + n]), ptr(jac), lam_reg * 0.25 / total_pn,
                                      lam_reg * 0.1 / total_pn, n, ptr(df), ptr(dfj), st), "dm_shade_bwd")
-            for pts_, d_ in ((g["pts"], df), (pj, dfj)):
+            for pts_, d_ in ((pts, df), (pj, dfj)):
                 check(lib().dm_hashgrid_mlp_bwd(C.byref(geo.hg), ptr(pts_), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(d_),
                                                 ptr(geo.dgrid), ptr(geo.dW1), ptr(geo.dW2), st), "hashgrid bwd")
         loss_reg = (0.25 * reg_sums[0] + 0.1 * reg_sums[1]) / total_pn

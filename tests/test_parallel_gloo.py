@@ -92,3 +92,56 @@ def test_shard_slice_validation():
         assert False
     except ValueError:
         pass
+
+
+def test_pixel_partition_covers_every_pixel_once():
+    from dreammat_b200.parallel import pixel_partition
+    for pn, world in (([10, 30, 5, 15], 2), ([10, 30, 5, 15, 7, 9, 100, 3], 4), ([57479, 91134, 197815, 120000, 80000, 64000, 150000, 99000], 8),
+                      ([5, 0, 7, 1], 4), ([3, 3], 1)):
+        segs, counts = pixel_partition(pn, world)
+        per = len(pn) // world
+        seen = [[0] * n for n in pn]
+        for r in range(world):
+            shaded = 0
+            for (g, a, b) in segs[r]:
+                assert 0 <= a < b <= pn[g]
+                for i in range(a, b):
+                    seen[g][i] += 1
+                shaded += b - a
+            assert shaded == sum(counts[r])
+            assert abs(shaded - sum(pn) / world) <= 1                      # equal intervals
+            # pieces are in global order, so the send buffer is already grouped by owner rank
+            owners = [g // per for (g, _, _) in segs[r]]
+            assert owners == sorted(owners)
+        assert all(c == 1 for row in seen for c in row)
+        for o in range(world):   # what rank o receives is exactly its own views' pixels
+            assert sum(counts[r][o] for r in range(world)) == sum(pn[o * per:(o + 1) * per])
+
+
+def _a2a_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from dreammat_b200.parallel import exchange_rows, pixel_partition
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pn = [7, 12, 3, 10]                      # 2 views per rank
+    segs, counts = pixel_partition(pn, world)
+    off = [0, 7, 19, 22, 32]
+    # "colour" of global pixel i is i: every rank shades its interval, owners must end up with their views in order
+    send = torch.cat([torch.arange(off[g] + a, off[g] + b, dtype=torch.float32) for (g, a, b) in segs[rank]]).view(-1, 1).repeat(1, 3)
+    recv_counts = [counts[r][rank] for r in range(world)]
+    own = exchange_rows(send, counts[rank], recv_counts, world)
+    lo, hi = off[rank * 2], off[rank * 2 + 2]
+    ok = torch.equal(own[:, 0], torch.arange(lo, hi, dtype=torch.float32))
+    back = exchange_rows(own * 2, recv_counts, counts[rank], world)           # the backward direction
+    ok = ok and torch.equal(back, send * 2)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_exchange_rows_roundtrip_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_a2a_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
