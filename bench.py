@@ -116,6 +116,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(device))
     from dreammat_b200 import _cabi
     _cabi.check(_cabi.lib().dm_device_check(local), "dm_device_check")   # fails loudly without the sm_100a library
+    if args.no_pdl:
+        _cabi.lib().dm_tune(b"pdl", 0)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     V = args.views
     assert V % world == 0, "global view batch must divide over the ranks"
@@ -370,6 +372,7 @@ def main():
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the dense kernels")
     ap.add_argument("--no-balance", action="store_true", help="multi-GPU: every rank shades only its own views")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner, nvcc/ninja chatter)

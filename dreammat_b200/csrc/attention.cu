@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     auto s_full = [&](int jj) { return s_full0 + 8u * (uint32_t)(jj & 1); };
     const uint32_t tmem_slot = o_full + 8u;
 
+    griddep_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int nkb = (p.Nk + AK - 1) / AK;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ld_shared_u32(tmem_slot);
+    griddep_wait();      // PDL: q/k/v written by the previous kernel are visible from here
     const uint32_t tmem_O = tmem + 128;
     auto tmem_S = [&](int jj) { return tmem + 64u * (uint32_t)(jj & 1); };
 
@@ -375,7 +377,7 @@ extern "C" int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batc
     static bool cfg_h = false, cfg_b = false;
     if (bf16) {
         if (!cfg_b) { DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); cfg_b = true; }
-        attention_kernel<__nv_bfloat16, 0><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        DM_CHECK_CUDA(dm_launch(attention_kernel<__nv_bfloat16, 0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, (cudaStream_t)stream, tq, tk, tv, p));
     } else {
         if (!cfg_h) {
             DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -383,9 +385,9 @@ extern "C" int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batc
             DM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
             cfg_h = true;
         }
-        if (g_attn_packed_exp == 1) attention_kernel<__half, 1><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-        else if (g_attn_packed_exp == 2) attention_kernel<__half, 2><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-        else attention_kernel<__half, 0><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        if (g_attn_packed_exp == 1) DM_CHECK_CUDA(dm_launch(attention_kernel<__half, 1>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, (cudaStream_t)stream, tq, tk, tv, p));
+        else if (g_attn_packed_exp == 2) DM_CHECK_CUDA(dm_launch(attention_kernel<__half, 2>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, (cudaStream_t)stream, tq, tk, tv, p));
+        else DM_CHECK_CUDA(dm_launch(attention_kernel<__half, 0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, (cudaStream_t)stream, tq, tk, tv, p));
     }
     DM_CHECK_LAUNCH();
     return DM_OK;

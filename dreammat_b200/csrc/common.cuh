@@ -23,6 +23,30 @@ void dm_count_launch();
         }                                                                            \
     } while (0)
 
+// ---- programmatic dependent launch (PDL).  Kernels of the dense section call griddep_launch_dependents() first
+// thing (the next kernel of the stream may then be scheduled as SM resources free up and run its prologue: barrier
+// init, TMEM allocation, tensor-map prefetch) and griddep_wait() before touching global memory written by earlier
+// kernels (it returns once every prerequisite grid has completed and flushed).  Both are no-ops for launches without
+// the attribute, so correctness never depends on the knob (dm_tune "pdl").
+extern int g_dm_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t dm_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = g_dm_pdl ? at : nullptr;
+    cfg.numAttrs = g_dm_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define DM_CHECK_LAUNCH()                                                            \
     do {                                                                             \
         dm_count_launch();                                                           \

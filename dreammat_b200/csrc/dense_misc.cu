@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
                                                        int chunks, int vslab, float* __restrict__ stats) {
     extern __shared__ float s_acc[];  // [G*2]
     const int img = blockIdx.y, cpg = C / G;
+    griddep_launch_dependents();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
+    griddep_wait();
     const GnIdx m = gn_index(HW, vslab, chunks);
     if (m.active) {
         float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        int chunks, int vslab, const float* __restrict__ stats,
                                                        const T* __restrict__ gamma, const T* __restrict__ beta,
                                                        float eps, int silu, T* __restrict__ y) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int img = blockIdx.y, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
     const GnIdx m = gn_index(HW, vslab, chunks);
@@ -158,9 +162,11 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
                                                            const T* __restrict__ beta, float eps, int silu,
                                                            float* __restrict__ bstats) {
     extern __shared__ float s_acc[];
+    griddep_launch_dependents();
     const int img = blockIdx.y, cpg = C / G;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
+    griddep_wait();
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
     const GnIdx m = gn_index(HW, vslab, chunks);
     if (m.active) {
@@ -222,6 +228,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
                                                            const T* __restrict__ gamma, const T* __restrict__ beta,
                                                            float eps, int silu, const T* __restrict__ dx_add,
                                                            T* __restrict__ dx) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int img = blockIdx.y, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
     const GnIdx m = gn_index(HW, vslab, chunks);
@@ -288,6 +296,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                                                         float eps, T* __restrict__ y) {
     // warp per row, 16-byte vectors (C % 8 == 0, C <= 1280 -> at most 5 vectors per lane kept in registers);
     // two-pass mean / centred variance on the register copy
+    griddep_launch_dependents();
+    griddep_wait();
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31, nv = C >> 3;
@@ -601,10 +611,10 @@ extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, i
     const int vslab = gn_vslab(C / 8), slabs = (C / 8) / vslab;
     const int chunks = gn_chunks(n_img, HW, slabs, 256 / vslab);
     const dim3 grid(chunks, n_img, slabs);
-    DM_DISPATCH_T(bf16, gn_stats_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>((const T*)x, HW, C, ld, G, chunks, vslab, stats));
+    DM_DISPATCH_T(bf16, DM_CHECK_CUDA(dm_launch(gn_stats_kernel<T>, grid, dim3(256), 2 * G * sizeof(float), st, (const T*)x, HW, C, ld, G, chunks, vslab, stats)));
     DM_CHECK_LAUNCH();
-    DM_DISPATCH_T(bf16, gn_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, HW, C, ld, ldy, G, chunks, vslab, stats, (const T*)gamma,
-                                                                (const T*)beta, eps, silu, (T*)y));
+    DM_DISPATCH_T(bf16, DM_CHECK_CUDA(dm_launch(gn_apply_kernel<T>, grid, dim3(256), 0, st, (const T*)x, HW, C, ld, ldy, G, chunks, vslab, (const float*)stats,
+                                                (const T*)gamma, (const T*)beta, eps, silu, (T*)y)));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -619,12 +629,11 @@ extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_i
     const int vslab = gn_vslab(C / 8), slabs = (C / 8) / vslab;
     const int chunks = gn_chunks(n_img, HW, slabs, 256 / vslab);
     const dim3 grid(chunks, n_img, slabs);
-    DM_DISPATCH_T(bf16, gn_bwd_stats_kernel<T><<<grid, 256, 2 * G * sizeof(float), st>>>(
-                            (const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats));
+    DM_DISPATCH_T(bf16, DM_CHECK_CUDA(dm_launch(gn_bwd_stats_kernel<T>, grid, dim3(256), 2 * G * sizeof(float), st,
+                            (const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats, (const T*)gamma, (const T*)beta, eps, silu, bstats)));
     DM_CHECK_LAUNCH();
-    DM_DISPATCH_T(bf16, gn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats, bstats,
-                                                                    (const T*)gamma, (const T*)beta, eps, silu,
-                                                                    (const T*)dx_add, (T*)dx));
+    DM_DISPATCH_T(bf16, DM_CHECK_CUDA(dm_launch(gn_bwd_apply_kernel<T>, grid, dim3(256), 0, st, (const T*)x, (const T*)dz, HW, C, G, chunks, vslab, stats,
+                                                (const float*)bstats, (const T*)gamma, (const T*)beta, eps, silu, (const T*)dx_add, (T*)dx)));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -634,8 +643,8 @@ extern "C" int dm_layernorm(int bf16, const void* x, int64_t M, int C, const voi
     DM_REQUIRE(x && gamma && beta && y, "null pointer");
     DM_REQUIRE(C <= 1280 && C % 8 == 0, "C <= 1280, multiple of 8");
     if (M == 0) return DM_OK;
-    DM_DISPATCH_T(bf16, layernorm_kernel<T><<<(unsigned)dm_ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, (const T*)gamma,
-                                                                                                        (const T*)beta, eps, (T*)y));
+    DM_DISPATCH_T(bf16, DM_CHECK_CUDA(dm_launch(layernorm_kernel<T>, dim3((unsigned)dm_ceil_div(M, 8)), dim3(256), 0, (cudaStream_t)stream,
+                                                (const T*)x, M, C, (const T*)gamma, (const T*)beta, eps, (T*)y)));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

@@ -3,6 +3,8 @@
 #include <vector>
 #include "common.cuh"
 
+int g_dm_pdl = 1;   // programmatic dependent launch for the dense-section kernels (dm_tune "pdl")
+
 static thread_local char g_err[512] = "";
 
 void dm_set_error(const char* fmt, ...) {

@@ -538,6 +538,7 @@ extern int g_bvh_leaf_max;
 extern "C" int dm_tune(const char* key, int value) {
     if (!key) return DM_EINVAL;
     if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    else if (!strcmp(key, "pdl")) g_dm_pdl = value ? 1 : 0;
     else if (!strcmp(key, "bvh_leaf")) g_bvh_leaf_max = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(key, "mc_refill") || !strcmp(key, "mc_leaf_batch")) { /* retired experiment knobs */ }
     else { dm_set_error("dm_tune: unknown key %s", key); return DM_EINVAL; }

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
 
+    griddep_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = p.K / BK;
     const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM - 1) / BM;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    griddep_wait();      // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here
 
     if (warp == 0) {
         if (lane == 0) {
@@ -384,6 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
 
+    griddep_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int nk = p.K / BK;
@@ -408,6 +411,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = ld_shared_u32(tmem_slot);
     cluster_sync_all();                                  // the peer's TMEM is allocated before the first MMA lands in it
+    griddep_wait();                                      // PDL: the previous kernel's outputs are visible from here
 
     if (warp == 0) {
         if (lane == 0) {
@@ -548,7 +552,7 @@ int launch_cps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams&
     int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
     int64_t slots = (int64_t)DM_NUM_SMS * CPS;
     unsigned grid = (unsigned)(tiles < slots ? tiles : slots);   // persistent: CPS CTAs per SM
-    kern<<<grid, NTHREADS, Cfg<BN, CPS>::SMEM, st>>>(tmA, tmB, p);
+    DM_CHECK_CUDA(dm_launch(kern, dim3(grid), dim3(NTHREADS), (size_t)Cfg<BN, CPS>::SMEM, st, tmA, tmB, p));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -584,6 +588,8 @@ bool ensure_ws(size_t floats, cudaStream_t st) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmParams p) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int64_t n4 = p.N >> 2;
     const int64_t total = (int64_t)(p.batch > 0 ? p.batch : 1) * p.M * n4;
     const T* bias = (const T*)p.bias;
@@ -655,7 +661,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     }
     int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, 2 * BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
     unsigned clusters = (unsigned)(tiles < max_clusters ? tiles : max_clusters);
-    kern<<<2 * clusters, NTHREADS, PairCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    DM_CHECK_CUDA(dm_launch(kern, dim3(2 * clusters), dim3(NTHREADS), (size_t)PairCfg<BN>::SMEM, st, tmA, tmB, p));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
@@ -729,8 +735,8 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p
     const int64_t work = batch * p.M * (p.N >> 2);
     int64_t blocks = dm_ceil_div(work, 256);
     if (blocks > DM_NUM_SMS * 8) blocks = DM_NUM_SMS * 8;
-    if (bf16) splitk_finish_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else splitk_finish_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(p);
+    if (bf16) DM_CHECK_CUDA(dm_launch(splitk_finish_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, st, p));
+    else DM_CHECK_CUDA(dm_launch(splitk_finish_kernel<__half>, dim3((unsigned)blocks), dim3(256), 0, st, p));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
