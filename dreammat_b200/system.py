@@ -172,8 +172,9 @@ class DreamMatMaterial:
         self.light = [R.envmap_pack(m.to(self.device)) for m in (env_maps or [])]
         self.tab_d = R.direction_tables(c.diffuse_sample_num).to(self.device)
         self.tab_s = R.direction_tables(c.specular_sample_num).to(self.device)
-        # visiting order of the samples: identity.  (R.sample_order's direction-coherent order measured ~7% slower with the
-        # persistent-ray traversal: rays of similar length finish together and starve the refill logic.)
+        # visiting order of the samples: identity = the Fibonacci tables' own order, sorted by elevation, so the 32 rays of a
+        # lock-step pass have similar traversal lengths.  Direction-coherent orders (R.sample_order, azimuth sectors) measured
+        # ~10 % slower (scripts/exp_shade_order.py).
         self.perm = None
         self.mc_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness_squre, c.max_roughness_squre,
                                   c.diffuse_sample_num, c.specular_sample_num)
