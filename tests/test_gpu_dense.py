@@ -74,6 +74,38 @@ def test_gemm_conv_match_torch_fp32():
             assert out.shape == (M, Dh) and rel(out, ref) < 1e-3, (M, Dh, bn, rel(out, ref))
 
 
+def test_pair_and_splitk_kernels_match_torch_fp32():
+    """CTA-pair (cta_group::2) tiles of every width, phantom second CTA (odd 128-row tile count), ragged N, stride-2
+    conv, and split-K (single-CTA and pair paths; run twice: the fp32 workspace must come back zeroed)."""
+    import torch.nn.functional as F
+    from dreammat_b200 import dense_ops as D
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (M, N, K, bn) in ((256, 128, 64, 1128), (300, 200, 192, 1128), (1000, 320, 320, 1160), (513, 768, 1024, 1256), (4096, 640, 640, 1256)):
+        a = torch.randn(M, K, device="cuda", generator=g).half(); b = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+        bias = torch.randn(N, device="cuda", generator=g).half(); res = torch.randn(M, N, device="cuda", generator=g).half()
+        out = D.gemm(a, b, bias=bias, residual=res, bn=bn)
+        ref = a.float() @ b.float().t() + bias.float() + res.float()
+        assert rel(out, ref) < 1e-3, (M, N, K, bn, rel(out, ref))
+    x = torch.randn(2, 64, 64, 64, device="cuda", generator=g).half()
+    w = (torch.randn(128, 64, 3, 3, device="cuda", generator=g) / 24).half()
+    y = D.conv2d(x, D.conv_weight_to_gemm(w), 3, stride=2, pad=(0, 0), out_hw=(32, 32), bn=1128)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), stride=2)
+    assert rel(nchw(y), ref) < 1e-3
+    # split-K: few tiles, long K (auto heuristics); 8x8 latents of a one-view batch
+    for (n, hw, ci, co) in ((3, 8, 1280, 1280), (3, 8, 2560, 1280), (3, 16, 1280, 1280)):
+        x = torch.randn(n, hw, hw, ci, device="cuda", generator=g).half()
+        w = (torch.randn(co, ci, 3, 3, device="cuda", generator=g) / 100).half()
+        tp = torch.randn(n, co, device="cuda", generator=g).half()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1) + tp.float()[:, :, None, None]
+        for _ in range(2):
+            y = D.conv2d(x, D.conv_weight_to_gemm(w), 3, rowvec=tp)
+            assert rel(nchw(y), ref) < 1e-3, (n, hw, ci, co, rel(nchw(y), ref))
+    a = torch.randn(192, 5120, device="cuda", generator=g).half(); b = (torch.randn(1280, 5120, device="cuda", generator=g) * 0.02).half()
+    ref = F.silu(a.float() @ b.float().t())
+    for _ in range(2):
+        assert rel(D.gemm(a, b, act="silu"), ref) < 1e-3
+
+
 def test_attention_matches_torch_fp32():
     import torch.nn.functional as F
     from dreammat_b200 import dense_ops as D
