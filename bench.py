@@ -225,7 +225,7 @@ def run_ours(args):
     if t_dense:
         ach = DENSE_TFLOP_PER_VIEW * Vl / (t_dense / 1000.0)
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
-                           "traffic": None, "kernel": "tc_gemm_kernel (+attention) over the dense section",
+                           "traffic": None, "kernel": "tc_gemm_pair_kernel + tc_gemm_kernel + attention_kernel over the dense section",
                            "peak_source": src + " sustained bf16"}
         out["sections_ms"] = sec
         # shading half: NOT HBM-bound (BVH traversal + FP32 ALU); reported so the fraction is computable:
