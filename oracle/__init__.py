@@ -5,11 +5,23 @@ function, each citing the reference file:line it follows.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may import this package; nothing under ``dreammat_b200/`` does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer
-fixtures for this path, and it cannot be imported in the build
-container (pytorch_lightning / diffusers / nvdiffrast / tinycudann / envlight /
-_raytracing are absent).  The only reference-held data the oracle is pinned against is
-``load/lights/bsdf_256_256.bin`` (tests/test_oracle_pins.py); everything else is
-pinned by self-consistency checks (brute force vs BVH, autograd vs finite
-differences, white-furnace, MC -> split-sum convergence).
+PARITY STATUS: pinned where the reference's own code can run, unpinned where it cannot.
+The reference ships no tests, golden vectors or known-answer fixtures
+and cannot be imported as a package in the build container (pytorch_lightning / omegaconf /
+diffusers / nvdiffrast / tinycudann / envlight / _raytracing are absent).  Its plain-torch
+function bodies CAN be executed: tests/golden/make_golden.py lifts them out of
+/root/reference by AST and runs them on seeded inputs; tests/test_oracle_golden.py pins this
+oracle against the resulting vectors (tests/golden/reference_vectors.pt) for
+  a1  collate / cameras / rays / mvp (data/uncond.py:723-821, utils/ops.py:179-292),
+  a2  ControlNet normal / depth maps (raytracing_renderer.py:326-343),
+  a3  tangent frame + position jitter (raytracing_renderer.py:161-173, 306-316),
+  a4  DreamMatMaterial.forward -> shade_raytracing, forward AND autograd backward, with the
+      reference's sampling tables, env lookup and occlusion semantics (dreammat_material.py),
+  a8/a9  the CSD combination, loss_sds and its gradient (dreammat_guidance.py:440-497, 584-602),
+  schedules C(), vertex normals, material export.
+PARITY UNPINNED for the arithmetic that lives inside absent native packages -- tiny-cuda-nn
+hash grid, nvdiffrast rasterise / antialias / texture, envlight cube maps, the _raytracing BVH,
+diffusers UNet / ControlNet / VAE: restated from their published form and pinned only by
+``load/lights/bsdf_256_256.bin``, the published parameter counts and self-consistency checks
+(brute force vs BVH, autograd vs finite differences, white furnace, MC -> split-sum convergence).
 """

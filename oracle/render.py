@@ -640,6 +640,26 @@ def vertex_normals(v, f):
     return F.normalize(vn, dim=-1)
 
 
+def controlnet_depth(depth, mask, min_val=0.3):
+    """raytracing_renderer.py:129-134 / compute_controlnet_depth :333-343: inverse depth of the covered pixels
+    rescaled to [min_val, 1] by their min / max, 0 elsewhere."""
+    depth = depth.clone()
+    dm = 1.0 / (depth[mask] + 1e-6)
+    depth[mask] = (1 - min_val) * (dm - dm.min()) / (dm.max() - dm.min() + 1e-6) + min_val
+    depth[~mask] = 0.0
+    return depth
+
+
+def controlnet_view_normals(normals, w2c):
+    """compute_controlnet_normals (raytracing_renderer.py:326-331) for one view: rotate into the camera frame
+    (xfm_vectors :69-83, w = 0), normalise, map to [0,1], flip x."""
+    n4 = torch.cat([normals, torch.zeros(normals.shape[0], 1)], -1)
+    nv = F.normalize((n4 @ w2c.t())[:, :3], dim=-1)
+    nc = 0.5 * (nv + 1)
+    nc[..., 0] = 1.0 - nc[..., 0]
+    return nc
+
+
 def gbuffer(tracer: RayTracer, v_pos, t_idx, v_nrm, rays_o, rays_d, mvp, w2c):
     """G-buffer stage of RaytraceRender.forward (raytracing_renderer.py:122-159).
 
@@ -668,16 +688,9 @@ def gbuffer(tracer: RayTracer, v_pos, t_idx, v_nrm, rays_o, rays_d, mvp, w2c):
     rast = torch.where(hit[:, None], rast, torch.zeros_like(rast)).reshape(B, H, W, 4)
     mask = rast[..., 3:] > 0
     # depth normalisation (:129-134), global min / max over the batch
-    depth = rast[..., 2:3].clone()
-    dm = 1.0 / (depth[mask] + 1e-6)
-    depth[mask] = 0.7 * (dm - dm.min()) / (dm.max() - dm.min() + 1e-6) + 0.3
+    depth = controlnet_depth(rast[..., 2:3], mask)
     # controlnet view normals (:139-147, :326-331) -- per view so B>1 is well defined (a0)
-    nv = torch.zeros(B, H * W, 3)
-    for b in range(B):
-        n4 = torch.cat([Nn.reshape(B, H * W, 3)[b], torch.zeros(H * W, 1)], -1)
-        nv[b] = F.normalize((n4 @ w2c[b].t())[:, :3], dim=-1)
-    nc = 0.5 * (nv + 1)
-    nc[..., 0] = 1.0 - nc[..., 0]
+    nc = torch.stack([controlnet_view_normals(Nn.reshape(B, H * W, 3)[b], w2c[b]) for b in range(B)])
     bg = torch.tensor([0.5, 0.5, 1.0])
     comp_normal = torch.where(mask.reshape(B, H * W, 1), nc, bg).reshape(B, H, W, 3)
     return dict(rast=rast, mask=mask, selector=mask[..., 0].reshape(B, H * W), gb_pos=P.reshape(B, H * W, 3),
