@@ -189,8 +189,13 @@ def geometry_forward(points, params, W1, W2, meta):
     utils/ops.py:26-37) and VanillaMLP bias-free 32->64->5 (models/networks.py:150-187)."""
     x01 = (points - (-1.0)) / (1.0 - (-1.0))
     enc = hashgrid_encode(x01, params, meta)
-    h = torch.relu(enc @ W1.t())
-    return h @ W2.t()
+    return mlp_forward(enc, W1, W2)
+
+
+def mlp_forward(enc, W1, W2):
+    """VanillaMLP (models/networks.py:150-187) as configured by dreammat.yaml: Linear(bias=False) -> ReLU ->
+    Linear(bias=False), output activation none; W1 = layers.0.weight [64,32], W2 = layers.2.weight [5,64]."""
+    return torch.relu(enc @ W1.t()) @ W2.t()
 
 
 # ----------------------------------------------------------------------------- material (a4)

@@ -15,6 +15,9 @@ What is covered (reference file:line -> golden key):
   models/renderers/raytracing_renderer.py:161-173,306-343 -> "jitter", "controlnet_maps" (a2/a3)
   models/materials/dreammat_material.py:89-123,490-677,713-797 -> "material" (a4 forward + autograd backward, export)
   models/guidance/dreammat_guidance.py:440-497,584-602    -> "guidance"     (a8/a9: CSD combination, loss_sds, its gradient)
+  models/prompt_processors/base.py:52-85,187-189,243-309  -> "prompt"       (a8: view-dependent embedding selection, [text|uncond|null])
+  models/guidance/dreammat_guidance.py:388-438            -> "branches"     (a8: CFG batch layout of the UNet call)
+  models/networks.py:150-187                              -> "mlp"          (a3: VanillaMLP structure, keys, forward)
   utils/misc.py:65-86                                     -> "C"            (schedules)
   models/mesh.py:135-161                                  -> "vertex_normals"
 Not coverable by execution (their arithmetic is inside absent native packages): tiny-cuda-nn hash grid, nvdiffrast
@@ -77,6 +80,32 @@ def lift(path, names, ns, cls=None):
     missing = set(names) - found
     assert not missing, (path, missing)
     return ns
+
+
+class _Sub:
+    """stands in for jaxtyping's Float[Tensor, "..."] in dataclass field annotations"""
+
+    def __class_getitem__(cls, item):
+        return cls
+
+
+def lift_class(path, cls, ns, keep_fields=False):
+    """exec a whole class definition of a reference file into ns (function annotations stripped; keep_fields leaves
+    the class-level annotated fields in place, for @dataclass definitions)."""
+    src = open(os.path.join(REF, path)).read()
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.ClassDef) and n.name == cls)
+    if keep_fields:
+        import dataclasses
+        import typing
+        ns.update({k: getattr(typing, k) for k in ("Callable", "List", "Dict", "Tuple", "Optional", "Any")})
+        ns.update(dataclass=dataclasses.dataclass, field=dataclasses.field, Float=_Sub, Bool=_Sub, Int=_Sub)
+        node.body = [(_Strip().visit(b) if isinstance(b, ast.FunctionDef) else b) for b in node.body]
+        mod = ast.Module(body=[node], type_ignores=[])
+    else:
+        mod = ast.Module(body=[_Strip().visit(node)], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, os.path.join(REF, path), "exec"), ns)
+    return ns[cls]
 
 
 def lift_block(path, first_marker, last_marker, ns, fn_name, args, ret):
@@ -253,6 +282,46 @@ def main():
                             "alphas": alphas, "scales": (1.05, -0.7, -0.2, 0.0)},
                      "out": {k: v.detach() for k, v in gout.items()} | {"d_latents": lat.grad.clone()}}
 
+    # ------------------------------------------------------------------ view-dependent prompt selection + CFG branch layout (a8)
+    npp = base_ns()
+    lift("models/prompt_processors/base.py", ["shift_azimuth_deg"], npp)
+    lift_class("models/prompt_processors/base.py", "DirectionConfig", npp, keep_fields=True)
+    lift("models/prompt_processors/base.py", ["configure"], npp, cls="PromptProcessor")
+    lift("models/prompt_processors/base.py", ["get_text_embeddings"], npp, cls="PromptProcessorOutput")
+    pp = Fake(cfg=Fake(view_dependent_prompt_front=False, front_threshold=45.0, back_threshold=45.0, overhead_threshold=60.0)).bind(npp, ["configure"])
+    try:
+        pp.configure()            # builds self.directions / direction2idx (:243-309), then reaches for load/prompt_library.json
+    except (FileNotFoundError, OSError):
+        pass
+    assert [d.name for d in pp.directions] == ["side", "front", "back", "overhead"]
+    Nv, Nt, Nf = 4, 5, 3
+    vd = torch.arange(Nv, dtype=torch.float32).view(Nv, 1, 1).expand(Nv, Nt, Nf).contiguous()
+    po = Fake(text_embeddings=vd[:1] + 100, uncond_text_embeddings=vd[:1] + 200, null_text_embeddings=vd[:1] + 300, text_embeddings_vd=vd + 10,
+              uncond_text_embeddings_vd=vd + 20, directions=pp.directions, direction2idx=pp.direction2idx).bind(npp, ["get_text_embeddings"])
+    el = torch.tensor([0.0, 0.0, 0.0, 0.0, 70.0, 0.0, 61.0, 10.0, -15.0, 59.9])
+    az = torch.tensor([90.0, 10.0, -44.0, 170.0, 10.0, -136.0, 179.0, 45.0, 225.0, 315.1])
+    dist = torch.ones_like(el)
+    G["prompt"] = {"elevation": el, "azimuth": az, "vd": po.get_text_embeddings(el, az, dist, True, return_null_text_embeddings=True),
+                   "no_vd": po.get_text_embeddings(el, az, dist, False, return_null_text_embeddings=True),
+                   "tables": {"text": po.text_embeddings, "uncond": po.uncond_text_embeddings, "null": po.null_text_embeddings,
+                              "text_vd": po.text_embeddings_vd, "uncond_vd": po.uncond_text_embeddings_vd}}
+    # branch layout of the noise prediction (compute_without_perpneg :388-438): latents x3, t x3, chunk(3) = text | uncond | null
+    lift("models/guidance/dreammat_guidance.py", ["compute_without_perpneg"], ng, cls="StableDiffusionLightGuidance")
+    import contextlib
+    rec = {}
+
+    def fake_unet(unet, x, t_, encoder_hidden_states=None, **kw):
+        rec.update(x=x.clone(), t=t_.clone(), ctx=encoder_hidden_states.clone())
+        return x * 2 + encoder_hidden_states.mean(dim=(1, 2)).view(-1, 1, 1, 1)
+    gw = Fake(cfg=Fake(view_dependent_prompting=True), unet=None, forward_unet=fake_unet,
+              disable_unet_class_embedding=lambda unet: contextlib.nullcontext(unet)).bind(ng, ["compute_without_perpneg"])
+    Bp = 3
+    zn = torch.randn(Bp, 4, 2, 2, generator=g)
+    tt = torch.tensor([5, 400, 900])
+    e_t, e_u, e_n = gw.compute_without_perpneg([0], po, zn, tt, el[:Bp], az[:Bp], dist[:Bp], [])
+    G["branches"] = {"latents_noisy": zn, "t": tt, "unet_in": rec["x"], "unet_t": rec["t"], "unet_ctx": rec["ctx"], "eps_text": e_t,
+                     "eps_uncond": e_u, "eps_null": e_n}
+
     # ------------------------------------------------------------------ schedules
     nc = base_ns(); nc["config_to_primitive"] = lambda v: list(v)
     lift("utils/misc.py", ["C"], nc)
@@ -267,6 +336,14 @@ def main():
     f = torch.randint(0, 30, (50, 3), generator=g)
     mesh = Fake(v_pos=v, t_pos_idx=f).bind(nv, ["_compute_vertex_normal"])
     G["vertex_normals"] = {"v": v, "f": f, "out": mesh._compute_vertex_normal()}
+
+    # ------------------------------------------------------------------ feature MLP (a3): module structure + forward
+    nn_ = base_ns(); nn_["get_activation"] = ns["get_activation"]
+    MLP = lift_class("models/networks.py", "VanillaMLP", nn_)
+    torch.manual_seed(5)
+    mlp = MLP(32, 5, {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64, "n_hidden_layers": 1})
+    enc = torch.randn(21, 32, generator=g)
+    G["mlp"] = {"state_dict": {k: v.detach().clone() for k, v in mlp.state_dict().items()}, "enc": enc, "out": mlp(enc).detach()}
 
     torch.save(G, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes; keys:", sorted(G))

@@ -143,6 +143,36 @@ def test_csd_combination_loss_and_gradient(G):
         assert close(v.norm(), go[k]), k
 
 
+def test_prompt_selection_and_cfg_branch_layout(G):
+    """a8: view-dependent embedding selection (prompt_processors/base.py:52-85 with the direction conditions of :243-309,
+    executed) and the CFG batch layout of the UNet call (dreammat_guidance.py:388-438): [text | uncond | null]."""
+    from dreammat_b200.guidance import PromptProcessorOutput, alphas_cumprod
+    g = G["prompt"]
+    t = g["tables"]
+    pu = PromptProcessorOutput(t["text"], t["uncond"], t["null"], t["text_vd"], t["uncond_vd"])
+    el, az = g["elevation"], g["azimuth"]
+    assert torch.equal(pu.get_text_embeddings(el, az, torch.ones_like(el), True, return_null_text_embeddings=True), g["vd"])
+    assert torch.equal(pu.get_text_embeddings(el, az, torch.ones_like(el), False, return_null_text_embeddings=True), g["no_vd"])
+    b = G["branches"]
+    B = b["latents_noisy"].shape[0]
+    assert torch.equal(b["unet_in"], torch.cat([b["latents_noisy"]] * 3)) and torch.equal(b["unet_t"], torch.cat([b["t"]] * 3))
+    assert torch.equal(b["unet_ctx"], pu.get_text_embeddings(el[:B], az[:B], torch.ones(B), True, return_null_text_embeddings=True))
+    out = b["unet_in"] * 2 + b["unet_ctx"].mean(dim=(1, 2)).view(-1, 1, 1, 1)          # the generator's stand-in UNet
+    for k, chunk in zip(("eps_text", "eps_uncond", "eps_null"), out.chunk(3)):
+        assert torch.equal(chunk, b[k]), k
+    assert close(alphas_cumprod(), G["guidance"]["in"]["alphas"])
+
+
+def test_feature_mlp_structure_and_forward(G):
+    """a3: VanillaMLP (models/networks.py:150-187) instantiated with dreammat.yaml's mlp_network_config: bias-free
+    Linear -> ReLU -> Linear; its state-dict keys are the checkpoint keys DreamMatMesh.state_dict uses."""
+    g = G["mlp"]
+    sd = g["state_dict"]
+    assert sorted(sd) == ["layers.0.weight", "layers.2.weight"]
+    assert tuple(sd["layers.0.weight"].shape) == (64, 32) and tuple(sd["layers.2.weight"].shape) == (5, 64)
+    assert close(OR.mlp_forward(g["enc"], sd["layers.0.weight"], sd["layers.2.weight"]), g["out"])
+
+
 def test_schedule_C(G):
     """utils/misc.py:65-86 against the oracle's and the product's C()."""
     from dreammat_b200.guidance import C
