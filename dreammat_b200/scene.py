@@ -144,8 +144,10 @@ class DataConfig:
 
 
 class FixCameraSet:
-    """The 128 fixed views of FixCameraIterableDataset (uncond.py:584-645, 692-698); camera/centre/up perturbs
-    are 0 in dreammat.yaml and omitted.  Draw order follows the reference so a shared CPU seed gives the same set."""
+    """The 128 fixed views of FixCameraIterableDataset (uncond.py:584-645, 692-698).  Draw order follows the reference
+    (elevations x2, azimuths, distances, camera / centre / up perturbs, fovy) so a shared CPU seed gives the same set --
+    pinned by tests/test_oracle_golden.py against the reference's own set_fix_* methods.  The perturbs are 0 in
+    dreammat.yaml: their three draws are consumed (they advance the generator before fovy) and discarded."""
 
     def __init__(self, cfg: DataConfig, generator: Optional[torch.Generator] = None):
         self.cfg = cfg
@@ -160,6 +162,9 @@ class FixCameraSet:
         self.azimuth_deg = (torch.rand(n, generator=g) + torch.arange(n)) / n * (a1 - a0) + a0
         d0, d1 = cfg.camera_distance_range
         self.camera_distances = torch.rand(n, generator=g) * (d1 - d0) + d0
+        torch.rand(n, 3, generator=g)       # camera_perturbs * 0   (uncond.py:623-628)
+        torch.randn(n, 3, generator=g)      # center_perturbs * 0   (:630-633)
+        torch.randn(n, 3, generator=g)      # up_perturbs * 0       (:635-639)
         f0, f1 = cfg.fovy_range
         self.fovy_deg = torch.rand(n, generator=g) * (f1 - f0) + f0
 

@@ -10,6 +10,7 @@ then pinned against these vectors by tests/test_oracle_golden.py -- on any machi
 Run from the repo root (only where /root/reference exists):  python tests/golden/make_golden.py
 
 What is covered (reference file:line -> golden key):
+  data/uncond.py:584-645,692-698                          -> "fixed_views"  (a1: the 128 fixed cameras, draw order)
   utils/ops.py:179-292, data/uncond.py:723-821            -> "collate"      (a1: cameras, rays, mvp, view/env draws)
   models/geometry/base.py:20-32, utils/ops.py:26-37       -> "contract"     (a3: contract_to_unisphere)
   models/renderers/raytracing_renderer.py:161-173,306-343 -> "jitter", "controlnet_maps" (a2/a3)
@@ -176,6 +177,18 @@ def main():
     G["collate"] = {"in": {k: getattr(ds, k) for k in ("elevation_degs", "azimuth_degs", "fix_camera_distances", "fovy_degs", "depths",
                                                       "normals", "lightmaps")} | {"H": H, "W": W, "seed": 123, "B": B},
                     "out": {k: v for k, v in out.items() if torch.is_tensor(v)}}
+
+    # ------------------------------------------------------------------ the fixed view set drawn at dataset construction (a1)
+    names = ["set_fix_elevs", "set_fix_azims", "set_fix_camera_distance", "set_fix_camera_perturb", "set_fix_center_perturb",
+             "set_fix_up_perturb", "set_fix_fovy"]
+    lift("data/uncond.py", names, ns, cls="FixCameraIterableDataset")
+    fv = Fake(cfg=Fake(fix_view_num=128, camera_perturb=0.0, center_perturb=0.0, up_perturb=0.0), elevation_range=(-20, 45),
+              azimuth_range=(-180, 180), camera_distance_range=(3, 4), fovy_range=(25, 45)).bind(ns, names)   # configs/dreammat.yaml:11-17
+    torch.manual_seed(2024)
+    for n_ in names:          # the call order of __init__ (uncond.py:692-698)
+        getattr(fv, n_)()
+    G["fixed_views"] = {"seed": 2024, "elevation_degs": fv.elevation_degs, "azimuth_degs": fv.azimuth_degs,
+                        "camera_distances": fv.fix_camera_distances, "fovy_degs": fv.fovy_degs}
 
     # ------------------------------------------------------------------ contract_to_unisphere (a3)
     lift("models/geometry/base.py", ["contract_to_unisphere"], ns)

@@ -50,6 +50,17 @@ def test_collate_cameras_rays_and_draws(G):
     assert torch.equal(v2, go["view_id"]) and torch.equal(e2, go["env_id"])
 
 
+def test_fixed_view_set_draw_order(G):
+    """a1: set_fix_elevs / azims / camera_distance / *_perturb / fovy in the order of __init__ (uncond.py:584-645,692-698):
+    with the reference's seed the product's FixCameraSet is the reference's camera set, fovy included (it is drawn after the
+    three zero-scaled perturb draws)."""
+    from dreammat_b200.scene import DataConfig, FixCameraSet
+    g = G["fixed_views"]
+    cams = FixCameraSet(DataConfig(width=32, height=32), torch.Generator().manual_seed(g["seed"]))
+    assert close(cams.elevation_deg, g["elevation_degs"]) and close(cams.azimuth_deg, g["azimuth_degs"])
+    assert close(cams.camera_distances, g["camera_distances"]) and close(cams.fovy_deg, g["fovy_degs"])
+
+
 def test_contract_to_unisphere_is_affine_for_radius_one(G):
     """a3: geometry/base.py:20-32 (bounded): the hash-grid input is (x - bmin) / (bmax - bmin); the oracle's
     geometry_forward and the CUDA kernel use exactly this map for radius 1."""
