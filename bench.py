@@ -24,6 +24,44 @@ DENSE_TFLOP_PER_VIEW = 5.50    # UNet 2.41 + ControlNet 
 UNET_CN_TFLOP_PER_VIEW = 3.27
 
 
+def burst_tflops():
+    """burst bf16/fp16 tensor peak for a kernel timed alone (MEASURED_PEAKS.json `bf16_tflops`), else the recipe's fallback"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["bf16_tflops"], "measured"
+    except Exception:
+        return 1650.0, "fallback"
+
+
+def kernel_roofline(dtype):
+    """Roofline of the dominant tensor kernel, timed ALONE with CUDA events on the launching stream: the CTA-pair
+    implicit-GEMM convolution on the UNet's 16x16-latent layer of the 8-view batch (conv3x3 24x16x16, 1280 -> 1280).
+    Algorithmic flops per launch = 2 * 6144 * 1280 * 11520; `traffic` is the DRAM read+write of the same launch from the
+    committed ncu --set full capture (profiles/r01c_launches_summary.md: 45.3 + 1.3 MB; algorithmic 29.5 MB weights +
+    15.7 MB input + 15.7 MB output, the nine taps re-read L2 only)."""
+    import torch
+    from dreammat_b200 import dense_ops as D
+    x = torch.randn(24, 16, 16, 1280, device="cuda").to(dtype)
+    w = (torch.randn(1280, 9 * 1280, device="cuda") * 0.01).to(dtype)
+    for _ in range(5):
+        D.conv2d(x, w, 3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 50
+    e0.record()
+    for _ in range(n):
+        D.conv2d(x, w, 3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * 24 * 256 * 1280 * 1280 * 9
+    peak, src = burst_tflops()
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 46.6e6,
+            "kernel": "tc_gemm_pair_kernel<256> conv3x3 24x16x16 1280->1280 (timed alone, %d launches, %.1f us each)" % (n, ms * 1e3),
+            "peak_source": src + " burst bf16", "traffic_source": "ncu --set full, profiles/r01c_launches_summary.md"}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -228,6 +266,10 @@ def run_ours(args):
                            "traffic": None, "kernel": "tc_gemm_pair_kernel + tc_gemm_kernel + attention_kernel over the dense section",
                            "peak_source": src + " sustained bf16"}
         out["sections_ms"] = sec
+        try:
+            out["roofline_kernel"] = kernel_roofline(dtype)
+        except Exception as ex:  # noqa: BLE001 -- the section-level roofline above stands on its own
+            out["roofline_kernel"] = {"error": str(ex)[:200]}
         # shading half: NOT HBM-bound (BVH traversal + FP32 ALU); reported so the fraction is computable:
         # algorithmic bytes = 200 B per covered pixel + one 16 B texel per unoccluded sample (upper bound: every sample)
         t_r = sec.get("render_fwd_ms")
