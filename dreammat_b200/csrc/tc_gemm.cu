@@ -501,6 +501,163 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------- halo-reuse 3x3 convolution (CTA pair)
+// EXPERIMENT, off by default (dm_tune_gemm 31 / 32).  For stride-1 3x3 convolutions whose output rows are >= 128 pixels
+// wide (the VAE's 512^2 / 256^2 / 128^2 levels) a 128-pixel M tile is one image-row segment, so the nine taps' A operands
+// are nine SHIFTED windows of one (3 rows x 130 pixels x 64 channels) halo tile: window (kh, kw) = 128 consecutive
+// 128-byte rows starting at row kh * 130 + kw of the halo.  The halo is fetched ONCE per 64-channel slab (one 4-D TMA
+// box, out-of-bounds rows / columns zero-filled = padding) instead of nine 16 KB tiles, and the UMMA descriptor's start
+// address is simply advanced by (kh * 130 + kw) * 128 bytes.  Per CTA and slab: 50 KB halo + 9 weight half-tiles instead of
+// 144 KB + 9 -- the N = 128 layers (operand-traffic bound at ~1.0 PFLOP/s today) drop from 96 to ~53 B/clk/SM.
+// HALO_MODE 1: descriptor base_offset = (start >> 7) & 7 (the 128B-swizzle phase of a start that is not 1024-byte aligned);
+// HALO_MODE 2: base_offset left 0 (if the hardware derives the phase from the address bits themselves).
+constexpr int HALO_W = 130, HALO_ROWS = 3 * HALO_W;
+constexpr int HALO_TX = HALO_ROWS * 128;                         // bytes one halo TMA delivers (49 920)
+constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;       // stage size, keeps 1024-byte alignment (51 200)
+template <int BN> struct HaloCfg {
+    static constexpr int HS = 2;                                 // halo stages
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    static constexpr int BS = BN == 256 ? 6 : 8;                 // weight half-tile stages
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int SMEM = HS * HALO_BYTES + BS * B_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = ACC_STAGES * BN;
+};
+
+template <int BN, typename T, int HALO_MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+    tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using C = HaloCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    griddep_launch_dependents();
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = smem_base + C::HS * HALO_BYTES;
+    const uint32_t bar_base = b_base + C::BS * C::B_BYTES;
+    auto full_h = [&](int s) { return bar_base + 8u * s; };
+    auto empty_h = [&](int s) { return bar_base + 8u * (C::HS + s); };
+    auto full_b = [&](int s) { return bar_base + 8u * (2 * C::HS + s); };
+    auto empty_b = [&](int s) { return bar_base + 8u * (2 * C::HS + C::BS + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::HS + 2 * C::BS + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::HS + 2 * C::BS + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::HS + 2 * C::BS + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int slabs = p.Cin / BK;
+    const int n_tiles = (p.N + BN - 1) / BN, m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+    const int total_tiles = n_tiles * m_pairs;
+    const int tiles_w = p.Wo / BM;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmH);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < C::HS; ++s) { mbar_init(full_h(s), 1); mbar_init(empty_h(s), 1); }
+        for (int s = 0; s < C::BS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    cluster_sync_all();
+    griddep_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer (both CTAs): halo(s+1) is requested before the nine
+            // weight tiles of slab s, so it lands while slab s is still being multiplied
+            int hs = 0; uint32_t hphase = 0; int bs = 0; uint32_t bphase = 0;
+            auto issue_halo = [&](int t, int slab) {
+                const int r = t;                                   // batch == 1
+                const int m_tile = (r / n_tiles) * 2 + (int)rank;
+                const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % p.Ho, tn = m_tile / (tiles_w * p.Ho);
+                mbar_wait(empty_h(hs), hphase ^ 1u);
+                if (rank == 0) mbar_expect_tx(full_h(hs), 2 * HALO_TX);
+                tma_load_4d_pair(smem_base + hs * HALO_BYTES, &tmH, full_h(hs) & PAIR_LEADER_MASK, slab * BK, tw * BM - 1, th - 1, tn);
+                if (++hs == C::HS) { hs = 0; hphase ^= 1u; }
+            };
+            // flattened stream of (tile, slab) pairs
+            int t = cluster_id, slab = 0;
+            bool have = t < total_tiles;
+            if (have) issue_halo(t, 0);
+            while (have) {
+                int nt = t, nslab = slab + 1;
+                if (nslab == slabs) { nslab = 0; nt = t + n_clusters; }
+                const bool have_next = nt < total_tiles;
+                if (have_next) issue_halo(nt, nslab);
+                const int n_tile = t % n_tiles;
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(empty_b(bs), bphase ^ 1u);
+                    if (rank == 0) mbar_expect_tx(full_b(bs), 2 * C::B_BYTES);
+                    tma_load_3d_pair(b_base + bs * C::B_BYTES, &tmB, full_b(bs) & PAIR_LEADER_MASK, (tap * slabs + slab) * BK,
+                                     n_tile * BN + (int)rank * (BN / 2), 0);
+                    if (++bs == C::BS) { bs = 0; bphase ^= 1u; }
+                }
+                t = nt; slab = nslab; have = have_next;
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA)
+            constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
+            constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)((2 * BM) >> 4) << 24);
+            int hs = 0; uint32_t hphase = 0; int bs = 0; uint32_t bphase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int slab = 0; slab < slabs; ++slab) {
+                    mbar_wait(full_h(hs), hphase);
+                    tc_fence_after();
+                    const uint32_t h_addr = smem_base + hs * HALO_BYTES;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(full_b(bs), bphase);
+                        tc_fence_after();
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const uint32_t a_addr = h_addr + (uint32_t)((kh * HALO_W + kw) * 128);
+                        uint64_t da = make_sw128_desc(a_addr);
+                        if (HALO_MODE == 1) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;     // swizzle phase of the shifted start
+                        const uint64_t db = make_sw128_desc(b_base + bs * C::B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (slab | tap | k) != 0);
+                        umma_commit_pair(empty_b(bs), 3);
+                        if (++bs == C::BS) { bs = 0; bphase ^= 1u; }
+                    }
+                    umma_commit_pair(empty_h(hs), 3);
+                    if (++hs == C::HS) { hs = 0; hphase ^= 1u; }
+                }
+                umma_commit_pair(tmem_full_bar(acc), 3);
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+            const int m_tile = (t / n_tiles) * 2 + (int)rank, n_tile = t % n_tiles;
+            const int64_t m = (int64_t)m_tile * BM + row;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_tile<BN, T, true>(p, tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16), m, 0, n_tile, lane,
+                                       tmem_empty_bar(acc) & PAIR_LEADER_MASK);
+            if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------- host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -783,11 +940,36 @@ void fill_epilogue(GemmParams& p, const dm_epilogue* e, int N) {
     p.out_f32 = e ? e->out_f32 : 0;
 }
 
+
+int g_gemm_halo = 0;   // 0 off, 1 / 2 = HALO_MODE of tc_conv_halo_kernel (dm_tune_gemm 30 / 31 / 32)
+
+template <int BN, typename T, int MODE>
+int launch_halo(const CUtensorMap& tmH, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = tc_conv_halo_kernel<BN, T, MODE>;
+    if (!configured) {
+        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<BN>::SMEM));
+        configured = true;
+    }
+    int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, 2 * BM);
+    unsigned clusters = (unsigned)(tiles < DM_NUM_SMS / 2 ? tiles : DM_NUM_SMS / 2);
+    DM_CHECK_CUDA(dm_launch(kern, dim3(2 * clusters), dim3(NTHREADS), (size_t)HaloCfg<BN>::SMEM, st, tmH, tmB, p));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+template <int BN>
+int dispatch_halo(const CUtensorMap& tmH, const CUtensorMap& tmB, const GemmParams& p, int bf16, cudaStream_t st) {
+    if (g_gemm_halo == 2) return bf16 ? launch_halo<BN, __nv_bfloat16, 2>(tmH, tmB, p, st) : launch_halo<BN, __half, 2>(tmH, tmB, p, st);
+    return bf16 ? launch_halo<BN, __nv_bfloat16, 1>(tmH, tmB, p, st) : launch_halo<BN, __half, 1>(tmH, tmB, p, st);
+}
+
 }  // namespace
 
 extern "C" int dm_tune_gemm(int code) {
     if (code >= 10 && code <= 12) g_gemm_pair = code - 10;      // CTA-pair kernel: 10 off, 11 heuristic, 12 always
     else if (code == 20 || code == 21) g_gemm_splitk = code - 20;  // split-K of few-tile long-K layers: off | on
+    else if (code >= 30 && code <= 32) g_gemm_halo = code - 30;    // halo-reuse 3x3 conv experiment: off | mode 1 | mode 2
     else g_gemm_cps = code == 1 ? 1 : 2;                        // single-CTA kernel: persistent CTAs per SM
     return DM_OK;
 }
@@ -849,6 +1031,32 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     DM_REQUIRE(tile_w * tile_h * tile_n == BM && Wo % tile_w == 0 && Ho % tile_h == 0,
                "output extent must tile into 128-pixel boxes (power-of-two sizes)");
     TileChoice tc = choose_tile((int64_t)n_img * Ho * Wo, Cout, ksize * ksize * Cin / BK, bn_hint, ep ? ep->act : 0);
+    if (g_gemm_halo && bn_hint == 0 && ksize == 3 && stride == 1 && pad_t == 1 && pad_l == 1 && Ho == H && Wo == W && Wo % BM == 0 &&
+        (Cout == 128 || Cout % 256 == 0) && (!ep || ep->act != 3) &&
+        dm_ceil_div((int64_t)n_img * Ho * Wo, 2 * BM) * dm_ceil_div(Cout, Cout == 128 ? 128 : 256) >= DM_NUM_SMS / 2) {
+        const int hbn = Cout == 128 ? 128 : 256;
+        CUtensorMap tmH, tmBh;
+        {
+            uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+            uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+            uint32_t box[4] = {BK, (uint32_t)HALO_W, 3, 1}, es[4] = {1, 1, 1, 1};
+            int rc = encode_map(&tmH, bf16, x, 4, dims, str, box, es); if (rc) return rc;
+        }
+        const int Kh = 9 * Cin;
+        {
+            uint64_t dims[3] = {(uint64_t)Kh, (uint64_t)Cout, 1};
+            uint64_t str[2] = {(uint64_t)Kh * 2, (uint64_t)Kh * Cout * 2};
+            uint32_t box[3] = {BK, (uint32_t)(hbn / 2), 1}, es[3] = {1, 1, 1};
+            int rc = encode_map(&tmBh, bf16, w, 3, dims, str, box, es); if (rc) return rc;
+        }
+        GemmParams p; memset(&p, 0, sizeof(p));
+        p.M = n_img * Ho * Wo; p.N = Cout; p.K = Kh; p.batch = 1; p.is_conv = 1; p.Cin = Cin; p.taps = 9; p.kw_n = 3;
+        p.Ho = Ho; p.Wo = Wo; p.tile_w = BM; p.tile_h = 1; p.tile_n = 1; p.stride = 1; p.pad_t = 1; p.pad_l = 1;
+        p.out = y; p.ldc = (int)ldc; p.out_batch_stride = 0;
+        fill_epilogue(p, ep, Cout);
+        return hbn == 128 ? dispatch_halo<128>(tmH, tmBh, p, bf16, (cudaStream_t)stream)
+                          : dispatch_halo<256>(tmH, tmBh, p, bf16, (cudaStream_t)stream);
+    }
     const int bn = tc.bn; const bool pair = tc.pair;
     CUtensorMap tmA, tmB;
     {
