@@ -1,6 +1,6 @@
 // tc_gemm.cu -- tcgen05 tensor-core GEMM / implicit-GEMM convolution for sm_100a.
 //
-// One kernel serves every dense contraction of the VAE encoder, the UNet and the ControlNet
+// Every dense contraction of the VAE encoder, the UNet and the ControlNet runs through this file
 // (rows a7/a8 of SURVEY.md section 8; reference call sites models/guidance/dreammat_guidance.py:
 // 218-229 ControlNetModel.forward, :274-282 UNet2DConditionModel.forward, :290 AutoencoderKL.encode,
 // which run cuDNN/cuBLAS kernels through diffusers):
@@ -14,14 +14,17 @@
 //                         Stride-2 convs use the map's element strides.
 //   * B = weights [N, K] (K-major), K index = tap * Cin + c.
 //
+// Three kernels share one epilogue (epilogue_tile: tcgen05.ld -> registers -> fused bias / per-image
+// vector / residual / SiLU / GELU / GEGLU / scale -> 16-byte global stores, or fp32 red.add for split-K):
+//   tc_gemm_kernel<BN,T,CPS>      one CTA per 128 x BN tile, 1-2 persistent CTAs per SM
+//   tc_gemm_pair_kernel<BN,T>     cta_group::2: a CTA pair per 256 x BN tile (the work-horse)
+//   tc_conv_halo_kernel<BN,T,M>   experiment: halo tile re-used across the nine taps (default off)
 // CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2-5 epilogue (tcgen05.ld -> registers -> fused bias / per-image vector / residual /
-// activation / scale -> 16-byte global stores).  Operand tiles are 128 x 64 (A) and BN x 64 (B)
-// in the 128-byte swizzled K-major layout shared by TMA and the UMMA descriptors; a ring of
-// mbarrier-guarded stages feeds the tensor core, tcgen05.commit releases stages and signals the
-// epilogue.  The kernel is persistent (one CTA per SM walks a strided list of tiles) with a double-buffered
-// TMEM accumulator, so the epilogue of tile i overlaps the main loop of tile i+1 and the TMA ring never drains
-// at tile boundaries.
+// warps 2-5 epilogue.  Operand tiles live in the 128-byte swizzled K-major layout shared by TMA and
+// the UMMA descriptors; a ring of mbarrier-guarded stages feeds the tensor core, tcgen05.commit
+// releases stages and signals the epilogue; the TMEM accumulator is double-buffered so the epilogue
+// of tile i overlaps the main loop of tile i+1.  choose_tile() picks kernel, tile width and split-K
+// from measured sweeps (profiles/r01_tile_sweep.txt, r01_exp_splitk.txt).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"

@@ -29,9 +29,11 @@ extern "C" {
 
 const char* dm_last_error(void);
 int dm_version(void);
-/* scheduling knobs for experiments: "mc_refill", "mc_leaf_batch", "mc_skip_horizon" */
+/* experiment knobs (no reference counterpart): "mc_skip_horizon" (0|1 skip below-horizon specular rays), "bvh_leaf" (1..4
+ * triangles per BVH leaf, takes effect at the next dm_bvh_build), "pdl" (0|1 programmatic dependent launch of the dense kernels) */
 int dm_tune(const char* key, int value);
-int dm_tune_attention(int packed_exp); /* experiment: ex2.approx.f16x2 softmax exponentials (fp16 only) */
+int dm_tune_attention(int mode);       /* softmax variant: 0 fp32 exponentials, rescale every block (default, fastest measured);
+                                      * 1 packed f16x2 exponentials + lazy rescale; 2 fp32 + lazy rescale */
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
                                       * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible;
                                       * 20|21: split-K of few-tile, long-K layers off | on;
