@@ -68,9 +68,20 @@ template <> struct Cvt<__nv_bfloat16> {
 // chunks of 32: acc*alpha + bias + rowvec -> act -> + residual -> * out_scale -> 16-byte stores.  `release_bar` is
 // arrived on (once per warp) as soon as the last chunk sits in registers, handing the TMEM buffer back to the MMA
 // issuer; REMOTE = the barrier lives in the leader CTA of a pair (shared::cluster address).
-template <int BN, typename T, bool REMOTE>
+// DUAL: the K loop alternated its MMAs between two accumulators (tmem_acc and tmem_acc + BN); their sum is the tile.
+template <int BN, typename T, bool REMOTE, bool DUAL = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int64_t m, int z, int n_tile,
                                               int lane, uint32_t release_bar) {
+    auto ld_acc = [&](uint32_t col, uint32_t (&v)[32]) {
+        tmem_ld_32x32b_x32(tmem_acc + col, v);
+        if constexpr (DUAL) {
+            uint32_t w2[32];
+            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)BN + col, w2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w2[j]));
+        }
+    };
     const bool row_ok = m < p.M;
     if (p.ws) {
         // split-K partial tile: accumulate raw fp32 sums; the epilogue proper runs in splitk_finish_kernel
@@ -78,7 +89,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+            ld_acc((uint32_t)c0, v);
             tmem_ld_wait();
             if (c0 + 32 >= BN) {
                 tc_fence_before();
@@ -111,8 +122,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64) {
             uint32_t v[32], g[32];
-            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
-            tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c0 + 32), g);
+            ld_acc((uint32_t)c0, v);
+            ld_acc((uint32_t)(c0 + 32), g);
             tmem_ld_wait();
             if (c0 + 64 >= BN) {
                 tc_fence_before();
@@ -141,7 +152,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)c0, v);
+        ld_acc((uint32_t)c0, v);
         tmem_ld_wait();
         if (c0 + 32 >= BN) {
             // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
@@ -231,11 +242,16 @@ template <int BN, int CPS> struct Cfg {
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // The TMA producer runs ahead across tile boundaries, the MMA warp alternates between two TMEM accumulators and the
 // epilogue warps drain accumulator i while the tensor pipe already works on accumulator i^1.
-template <int BN, typename T, int CPS>
+// DUAL = two accumulators per tile: even k-steps accumulate into one, odd k-steps into the other (two independent
+// dependency chains for the single issuing thread); the epilogue adds them.
+template <int BN, typename T, int CPS, bool DUAL = false>
 __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const GemmParams p) {
     using C = Cfg<BN, CPS>;
+    constexpr int ACC_W = DUAL ? 2 * BN : BN;                                  // TMEM columns per accumulator stage
+    constexpr int TCOLS = (C::ACC_STAGES * ACC_W) < 32 ? 32 : (C::ACC_STAGES * ACC_W);
+    static_assert(TCOLS * CPS <= 512, "TMEM budget");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -261,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
         for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
                 const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_W);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -325,7 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes along K inside the 128-byte swizzle atom = +2 in the (addr >> 4) field
-                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
+                        umma_f16(tmem_d + ((DUAL && (k & 1)) ? (uint32_t)BN : 0u), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                 DUAL ? ((kb > kb0) || (k >= 2)) : (((kb - kb0) | k) != 0));
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -346,14 +363,14 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             const int64_t m = (int64_t)m_tile * BM + row;
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile<BN, T, false>(p, tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16), m, z, n_tile,
+            epilogue_tile<BN, T, false, DUAL>(p, tmem_base + (uint32_t)(acc * ACC_W) + ((uint32_t)(quarter * 32) << 16), m, z, n_tile,
                                         lane, tmem_empty_bar(acc));
             if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
 
@@ -701,10 +718,12 @@ int encode_map(CUtensorMap* m, int bf16, const void* base, int rank, const uint6
 
 int g_gemm_cps = 2;   // persistent CTAs per SM for BN <= 128 (dm_tune "gemm_cps")
 
-template <int BN, typename T, int CPS>
+int g_gemm_dual = 0;   // two accumulators per tile in the single-CTA kernel for BN <= 128 (dm_tune_gemm 40 / 41)
+
+template <int BN, typename T, int CPS, bool DUAL = false>
 int launch_cps(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_gemm_kernel<BN, T, CPS>;
+    auto kern = tc_gemm_kernel<BN, T, CPS, DUAL>;
     if (!configured) {
         DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CPS>::SMEM));
         configured = true;
@@ -723,7 +742,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         // two co-resident CTAs only pay when there are more tiles than SMs; otherwise one CTA per SM with the full
         // 192 KB ring (twice the loads in flight) hides the L2/HBM latency of the long-K, few-tile layers better
         int64_t tiles = dm_ceil_div(p.N, BN) * dm_ceil_div(p.M, BM) * (p.batch > 0 ? p.batch : 1) * (p.split_k > 1 ? p.split_k : 1);
-        if (g_gemm_cps == 2 && tiles > DM_NUM_SMS) return launch_cps<BN, T, 2>(tmA, tmB, p, st);
+        const bool two = g_gemm_cps == 2 && tiles > DM_NUM_SMS;
+        if (g_gemm_dual && p.act != 3) {
+            if constexpr (BN == 64) { if (two) return launch_cps<BN, T, 2, true>(tmA, tmB, p, st); }
+            return launch_cps<BN, T, 1, true>(tmA, tmB, p, st);      // 128-wide dual needs all 512 TMEM columns
+        }
+        if (two) return launch_cps<BN, T, 2>(tmA, tmB, p, st);
     }
     return launch_cps<BN, T, 1>(tmA, tmB, p, st);
 }
@@ -972,6 +996,7 @@ int dispatch_halo(const CUtensorMap& tmH, const CUtensorMap& tmB, const GemmPara
 extern "C" int dm_tune_gemm(int code) {
     if (code >= 10 && code <= 12) g_gemm_pair = code - 10;      // CTA-pair kernel: 10 off, 11 heuristic, 12 always
     else if (code == 20 || code == 21) g_gemm_splitk = code - 20;  // split-K of few-tile long-K layers: off | on
+    else if (code == 40 || code == 41) g_gemm_dual = code - 40;    // two accumulators per tile (single-CTA kernel, BN <= 128): off | on
     else if (code >= 30 && code <= 32) g_gemm_halo = code - 30;    // halo-reuse 3x3 conv experiment: off | mode 1 | mode 2
     else g_gemm_cps = code == 1 ? 1 : 2;                        // single-CTA kernel: persistent CTAs per SM
     return DM_OK;

@@ -37,7 +37,8 @@ int dm_tune_attention(int mode);       /* softmax variant: 0 fp32 exponentials, 
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
                                       * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible;
                                       * 20|21: split-K of few-tile, long-K layers off | on;
-                                      * 30|31|32: halo-reuse 3x3 convolution kernel (experiment) off | descriptor mode 1 | mode 2 */
+                                      * 30|31|32: halo-reuse 3x3 convolution kernel (experiment) off | descriptor mode 1 | mode 2;
+                                      * 40|41: two accumulators per tile in the single-CTA kernel (experiment) off | on */
 /* number of kernels this library has launched in the process (bench.py's gpu_launches) */
 long long dm_launch_count(void);
 /* device sanity: returns 0 iff device `dev` is compute capability 10.x (sm_100a code present). */
