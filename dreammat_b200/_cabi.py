@@ -42,6 +42,8 @@ SIGNATURES = {
     "dm_launch_count": (C.c_longlong, []),
     "dm_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "dm_tune_gemm": (C.c_int, [C.c_int]),
+    "dm_gemm_workspace_bytes": (C.c_size_t, []),
+    "dm_gemm_set_workspace": (C.c_int, [P, C.c_size_t]),
     "dm_tune_attention": (C.c_int, [C.c_int]),
     "dm_device_check": (C.c_int, [C.c_int]),
     "dm_hashgrid_layout": (I64, [P, P]),

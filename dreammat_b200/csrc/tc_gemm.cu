@@ -757,18 +757,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
 float* g_ws = nullptr;
 size_t g_ws_floats = 0;
 int g_gemm_splitk = 1;
-constexpr size_t WS_FLOATS = 8u << 20;   // 32 MB: M*N <= 8 M elements
+constexpr size_t WS_FLOATS = 8u << 20;   // recommended size, 32 MB: M*N <= 8 M elements (dm_gemm_workspace_bytes)
 
-bool ensure_ws(size_t floats, cudaStream_t st) {
-    if (floats > WS_FLOATS) return false;
-    if (g_ws) return true;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
-    if (cudaMalloc(&g_ws, WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); g_ws = nullptr; return false; }
-    if (cudaMemset(g_ws, 0, WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); cudaFree(g_ws); g_ws = nullptr; return false; }
-    g_ws_floats = WS_FLOATS;
-    return true;
-}
+// The workspace is owned by the caller (dm_gemm_set_workspace): no hidden allocation inside the library.  Without one,
+// split-K is simply not used.
+bool ensure_ws(size_t floats, cudaStream_t) { return g_ws != nullptr && floats <= g_ws_floats; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const GemmParams p) {
@@ -872,7 +865,7 @@ TileChoice choose_tile(int64_t M, int N, int nk, int bn_hint, int act) {
             // few tiles: the layer is bound by L2->SMEM bytes (~12 TB/s chip-wide), which wide pair tiles cut 2-3x
             // against 64-wide tiles; split-K spreads the K loop over the idle TPCs
             // (the workspace pass costs ~10 us: only long K loops amortise it -- measured in scripts/exp_splitk.py)
-            if (g_gemm_splitk && act != 3 && (N & 3) == 0 && (nk >= 128 || (nk >= 64 && pt <= 8)) && (size_t)(M * N) <= WS_FLOATS) {
+            if (g_gemm_splitk && act != 3 && (N & 3) == 0 && (nk >= 128 || (nk >= 64 && pt <= 8)) && g_ws != nullptr && (size_t)(M * N) <= g_ws_floats) {
                 int64_t sp = tpcs / pt;
                 if (sp > nk / 8) sp = nk / 8;
                 if (sp > 16) sp = 16;
@@ -992,6 +985,14 @@ int dispatch_halo(const CUtensorMap& tmH, const CUtensorMap& tmB, const GemmPara
 }
 
 }  // namespace
+
+extern "C" size_t dm_gemm_workspace_bytes(void) { return WS_FLOATS * sizeof(float); }
+
+extern "C" int dm_gemm_set_workspace(void* ptr, size_t bytes) {
+    g_ws = (float*)ptr;
+    g_ws_floats = ptr ? bytes / sizeof(float) : 0;
+    return DM_OK;
+}
 
 extern "C" int dm_tune_gemm(int code) {
     if (code >= 10 && code <= 12) g_gemm_pair = code - 10;      // CTA-pair kernel: 10 off, 11 heuristic, 12 always

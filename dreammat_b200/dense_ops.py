@@ -43,9 +43,25 @@ def _is_bf16(t):
     raise TypeError(f"dense path expects fp16/bf16, got {t.dtype}")
 
 
+_WORKSPACE = {}
+
+
+def _ensure_workspace():
+    """Hand the library its split-K scratch (a zero-filled torch buffer, owned here) once per process; skipped while a
+    CUDA graph is being captured -- the eager warm-up that precedes every capture has already done it."""
+    dev = torch.cuda.current_device()
+    if dev in _WORKSPACE or torch.cuda.is_current_stream_capturing():
+        return
+    n = int(lib().dm_gemm_workspace_bytes())
+    buf = torch.zeros(n // 4, device=f"cuda:{dev}", dtype=torch.float32)
+    check(lib().dm_gemm_set_workspace(ptr_any(buf), n), "dm_gemm_set_workspace")
+    _WORKSPACE[dev] = buf
+
+
 def gemm(a, b, bias=None, rowvec=None, rows_per_vec=1, residual=None, alpha=1.0, out_scale=1.0, act=None,
          out=None, out_f32=False, bn=0):
     """a [.., M, K] @ b [.., N, K]^T -> [.., M, N].  Leading dim (if any) is a batch; b may be 2-D (shared)."""
+    _ensure_workspace()
     bf = _is_bf16(a)
     assert b.dtype == a.dtype
     batched = a.dim() == 3
@@ -80,6 +96,7 @@ def conv2d(x, w, ksize, stride=1, pad=(1, 1), out_hw=None, bias=None, rowvec=Non
            act=None, out=None, out_f32=False, bn=0):
     """x [n,H,W,Cin] NHWC (contiguous), w [Cout, k*k*Cin] -> y [n,Ho,Wo,Cout] (or into `out`, whose last-dim
     stride must be 1; its pixel stride gives ldc so it can be a channel slice of a wider buffer)."""
+    _ensure_workspace()
     bf = _is_bf16(x)
     assert x.is_contiguous() and w.is_contiguous()
     n, H, W, Cin = x.shape

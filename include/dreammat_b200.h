@@ -34,6 +34,10 @@ int dm_version(void);
 int dm_tune(const char* key, int value);
 int dm_tune_attention(int mode);       /* softmax variant: 0 fp32 exponentials, rescale every block (default, fastest measured);
                                       * 1 packed f16x2 exponentials + lazy rescale; 2 fp32 + lazy rescale */
+/* split-K scratch: a caller-owned, ZERO-FILLED device buffer of fp32 partial sums (the finish kernel re-zeroes what it
+ * reads, so it stays zero between calls).  Without a workspace split-K is not used.  One per process / device. */
+size_t dm_gemm_workspace_bytes(void);
+int dm_gemm_set_workspace(void* device_ptr, size_t bytes);
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
                                       * 10|11|12: CTA-pair (cta_group::2) kernel off | heuristic | wherever possible;
                                       * 20|21: split-K of few-tile, long-K layers off | on;
