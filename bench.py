@@ -382,7 +382,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "SDS iters/sec at 512x512, 8-view batch", "value": its, "unit": "it/s",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
            "ms_per_step": 1000.0 / its, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": {"workload": "north-star: %dx%d, %d-view batch" % (args.res, args.res, args.views)},
+           "data": "synthetic", "config": {"workload": "north-star: %dx%d, %d-view batch, 200+128 MC rays/px (oracle port on the host cores, bounded sample scaled to the full step)" % (args.res, args.res, args.views),
+                                           "views": args.views, "resolution": args.res},
            "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": "port", "sample": SAMPLE_DESC},
            "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
