@@ -12,6 +12,7 @@ Blender pre-rendering and mesh file formats stay outside (north_star: untouched)
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
@@ -198,6 +199,68 @@ class FixCameraSet:
         view_id = torch.floor(torch.rand(B, generator=generator) * self.cfg.fix_view_num).long()
         env_id = torch.floor(torch.rand(B, generator=generator) * self.cfg.fix_env_num).long()
         return view_id, env_id
+
+
+class FixViewMaps:
+    """The pre-rendered condition maps of `FixCameraIterableDataset.render_fixview_imgs` (data/uncond.py:532-582), read
+    from the reference's directory layout
+
+        <root>/depth/%03d.png                         16-bit PNG, millimetres
+        <root>/normal/%03d.png                        8-bit RGB
+        <root>/light/%03d_m{0.0,1.0}r{0.0,0.5,1.0}_env{1..E}.png   8-bit RGB, six per (view, env)
+
+    with the reference's arithmetic: RGB = INTER_AREA resize -> BGR2RGB -> / 255; depth = / 1000 -> INTER_NEAREST resize ->
+    inverse depth of the covered pixels rescaled to [0.3, 1] by their min / max (:540-557).  Row N1 of SURVEY.md section 8f:
+    the RGB maps are kept as the uint8 the resize produced (3.0 GB for 128 views x 5 envs at 512^2 instead of 12.1 GB of
+    fp32 -- `x / 255` of the stored byte is bit-identical to the reference's float map), optionally resident on the device,
+    and `condition_map` gathers [depth | normal | m0r0 m0r.5 m0r1 m1r0 m1r.5 m1r1] for the (view, env) pairs of a batch
+    (:799-802)."""
+
+    LIGHT_TAGS = ("m0.0r0.0", "m0.0r0.5", "m0.0r1.0", "m1.0r0.0", "m1.0r0.5", "m1.0r1.0")
+
+    def __init__(self, root: str, n_views: int, n_envs: int, height: int, width: int, device="cpu"):
+        import cv2
+        dim = (width, height)
+        self.depths = torch.zeros(n_views, height, width, 1)
+        self.normals = torch.zeros(n_views, height, width, 3, dtype=torch.uint8)
+        self.lightmaps = torch.zeros(n_views, n_envs, height, width, 18, dtype=torch.uint8)
+
+        def rgb_u8(path):
+            img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+            if img is None:
+                raise FileNotFoundError(path)
+            img = cv2.resize(img, dim, interpolation=cv2.INTER_AREA)
+            return torch.from_numpy(np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB)))
+
+        def depth_f32(path):
+            raw = cv2.imread(path, cv2.IMREAD_ANYDEPTH)
+            if raw is None:
+                raise FileNotFoundError(path)
+            depth = cv2.resize(raw / 1000, dim, interpolation=cv2.INTER_NEAREST)
+            mask = depth > 0
+            if mask.sum() <= 0:
+                return torch.from_numpy(depth[..., None])
+            inv = 1.0 / (depth + 1e-6)
+            dmax, dmin = inv[mask].max(), inv[mask].min()
+            depth[mask] = (1 - 0.3) * (inv[mask] - dmin) / (dmax - dmin + 1e-6) + 0.3
+            return torch.from_numpy(depth[..., None])
+
+        for v in range(n_views):
+            self.depths[v] = depth_f32(os.path.join(root, "depth", f"{v:03d}.png"))
+            self.normals[v] = rgb_u8(os.path.join(root, "normal", f"{v:03d}.png"))
+            for e in range(1, n_envs + 1):
+                self.lightmaps[v, e - 1] = torch.cat([rgb_u8(os.path.join(root, "light", f"{v:03d}_{tag}_env{e}.png"))
+                                                      for tag in self.LIGHT_TAGS], -1)
+        self.to(device)
+
+    def to(self, device):
+        self.depths, self.normals, self.lightmaps = (t.to(device) for t in (self.depths, self.normals, self.lightmaps))
+        return self
+
+    def condition_map(self, view_id: torch.Tensor, env_id: torch.Tensor) -> torch.Tensor:
+        """[B, H, W, 22] fp32 on the maps' device; channel order of uncond.py:581-582, :802."""
+        v, e = view_id.to(self.depths.device), env_id.to(self.depths.device)
+        return torch.cat((self.depths[v], self.normals[v].float() / 255.0, self.lightmaps[v, e].float() / 255.0), -1)
 
 
 def synthetic_envmap(H=512, W=1024, seed=0) -> torch.Tensor:

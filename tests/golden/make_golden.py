@@ -11,6 +11,7 @@ Run from the repo root (only where /root/reference exists):  python tests/golden
 
 What is covered (reference file:line -> golden key):
   data/uncond.py:584-645,692-698                          -> "fixed_views"  (a1: the 128 fixed cameras, draw order)
+  data/uncond.py:532-557 (loadrgb / loaddepth)            -> "maps"         (a1 / N1: condition-map PNG decoding)
   utils/ops.py:179-292, data/uncond.py:723-821            -> "collate"      (a1: cameras, rays, mvp, view/env draws)
   models/geometry/base.py:20-32, utils/ops.py:26-37       -> "contract"     (a3: contract_to_unisphere)
   models/renderers/raytracing_renderer.py:161-173,306-343 -> "jitter", "controlnet_maps" (a2/a3)
@@ -189,6 +190,29 @@ def main():
         getattr(fv, n_)()
     G["fixed_views"] = {"seed": 2024, "elevation_degs": fv.elevation_degs, "azimuth_degs": fv.azimuth_degs,
                         "camera_distances": fv.fix_camera_distances, "fovy_degs": fv.fovy_degs}
+
+    # ------------------------------------------------------------------ condition-map files (a1 / N1): loadrgb, loaddepth
+    import tempfile
+    import cv2
+    nl = base_ns(); nl["cv2"] = cv2
+    lift("data/uncond.py", ["loadrgb", "loaddepth"], nl, cls="FixCameraIterableDataset")      # nested in render_fixview_imgs
+    rng = np.random.RandomState(3)
+    src_hw, dst_hw = 48, 32                                              # files are rendered larger than the training size
+    yy, xx = np.mgrid[0:src_hw, 0:src_hw]
+    disk = ((yy - 24) ** 2 + (xx - 22) ** 2) < 17 ** 2
+    depth_mm = np.where(disk, 2500 + 40 * yy + 15 * xx + rng.randint(0, 30, (src_hw, src_hw)), 0).astype(np.uint16)
+    rgb_files = {"normal": rng.randint(0, 256, (src_hw, src_hw, 3)).astype(np.uint8)}
+    for tag in ("m0.0r0.0", "m0.0r0.5", "m0.0r1.0", "m1.0r0.0", "m1.0r0.5", "m1.0r1.0"):
+        rgb_files[tag] = rng.randint(0, 256, (src_hw, src_hw, 3)).astype(np.uint8)
+    with tempfile.TemporaryDirectory() as td:
+        cv2.imwrite(os.path.join(td, "d.png"), depth_mm)
+        d_out = nl["loaddepth"](os.path.join(td, "d.png"), (dst_hw, dst_hw))
+        rgb_out = {}
+        for k, arr in rgb_files.items():
+            cv2.imwrite(os.path.join(td, "c.png"), arr)                  # cv2 writes the array as BGR
+            rgb_out[k] = torch.from_numpy(nl["loadrgb"](os.path.join(td, "c.png"), (dst_hw, dst_hw)))
+    G["maps"] = {"depth_png_u16": torch.from_numpy(depth_mm.astype(np.int32)), "rgb_png_u8": {k: torch.from_numpy(v) for k, v in rgb_files.items()},
+                 "size": dst_hw, "depth": torch.from_numpy(d_out).float(), "rgb": rgb_out}
 
     # ------------------------------------------------------------------ contract_to_unisphere (a3)
     lift("models/geometry/base.py", ["contract_to_unisphere"], ns)

@@ -61,6 +61,29 @@ def test_fixed_view_set_draw_order(G):
     assert close(cams.camera_distances, g["camera_distances"]) and close(cams.fovy_deg, g["fovy_degs"])
 
 
+def test_condition_map_files_decode_like_the_reference(G, tmp_path):
+    """a1 / N1: the reference's nested loadrgb / loaddepth (data/uncond.py:532-557) executed on PNG files; FixViewMaps reads the
+    same files (reference directory layout), keeps RGB as uint8 and must reproduce the float maps bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from dreammat_b200.scene import FixViewMaps
+    g = G["maps"]
+    for sub in ("depth", "normal", "light"):
+        (tmp_path / sub).mkdir()
+    cv2.imwrite(str(tmp_path / "depth" / "000.png"), g["depth_png_u16"].numpy().astype(np.uint16))
+    cv2.imwrite(str(tmp_path / "normal" / "000.png"), g["rgb_png_u8"]["normal"].numpy())
+    for tag in FixViewMaps.LIGHT_TAGS:
+        cv2.imwrite(str(tmp_path / "light" / f"000_{tag}_env1.png"), g["rgb_png_u8"][tag].numpy())
+    maps = FixViewMaps(str(tmp_path), 1, 1, g["size"], g["size"])
+    cm = maps.condition_map(torch.tensor([0]), torch.tensor([0]))
+    assert cm.shape == (1, g["size"], g["size"], 22)
+    assert torch.equal(cm[0, ..., 0:1], g["depth"])
+    assert torch.equal(cm[0, ..., 1:4], g["rgb"]["normal"])
+    for i, tag in enumerate(FixViewMaps.LIGHT_TAGS):
+        assert torch.equal(cm[0, ..., 4 + 3 * i: 7 + 3 * i], g["rgb"][tag]), tag
+    assert maps.lightmaps.dtype == torch.uint8 and maps.normals.dtype == torch.uint8
+
+
 def test_contract_to_unisphere_is_affine_for_radius_one(G):
     """a3: geometry/base.py:20-32 (bounded): the hash-grid input is (x - bmin) / (bmax - bmin); the oracle's
     geometry_forward and the CUDA kernel use exactly this map for radius 1."""
