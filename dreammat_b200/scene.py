@@ -263,6 +263,23 @@ class FixViewMaps:
         return torch.cat((self.depths[v], self.normals[v].float() / 255.0, self.lightmaps[v, e].float() / 255.0), -1)
 
 
+def load_hdr_image(path: str) -> torch.Tensor:
+    """`load_hdr_image` (dreammat_material.py:65-68): lat-long radiance map (EXR / HDR) as RGB float32 [H, W, 3]."""
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_ANYCOLOR | cv2.IMREAD_ANYDEPTH)
+    if img is None:
+        raise FileNotFoundError(path)
+    return torch.from_numpy(np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB))).float()
+
+
+def load_reference_envmaps(environment_texture: str, n: int = 5):
+    """The five lat-long maps `DreamMatMaterial.configure` reads (dreammat_material.py:379-386):
+    <environment_texture>/map{i}/map{i}.exr, i = 1..5 -> list of [H, W, 3] float32 (the `env_maps` argument of
+    dreammat_b200.system.DreamMatMaterial)."""
+    return [load_hdr_image(os.path.join(environment_texture, f"map{i}", f"map{i}.exr")) for i in range(1, n + 1)]
+
+
 def synthetic_envmap(H=512, W=1024, seed=0) -> torch.Tensor:
     """HDR lat-long map standing in for load/lights/envmap/map{1..5}.exr (100 MB each; absent on the GPU box)."""
     g = torch.Generator().manual_seed(seed)

@@ -11,6 +11,7 @@ Run from the repo root (only where /root/reference exists):  python tests/golden
 
 What is covered (reference file:line -> golden key):
   data/uncond.py:584-645,692-698                          -> "fixed_views"  (a1: the 128 fixed cameras, draw order)
+  models/materials/dreammat_material.py:65-68             -> "envmap"       (a4 input: EXR decoding of the shipped map1.exr)
   data/uncond.py:532-557 (loadrgb / loaddepth)            -> "maps"         (a1 / N1: condition-map PNG decoding)
   utils/ops.py:179-292, data/uncond.py:723-821            -> "collate"      (a1: cameras, rays, mvp, view/env draws)
   models/geometry/base.py:20-32, utils/ops.py:26-37       -> "contract"     (a3: contract_to_unisphere)
@@ -22,6 +23,7 @@ What is covered (reference file:line -> golden key):
   models/networks.py:150-187                              -> "mlp"          (a3: VanillaMLP structure, keys, forward)
   utils/misc.py:65-86                                     -> "C"            (schedules)
   models/mesh.py:135-161                                  -> "vertex_normals"
+  models/geometry/dreammat_mesh.py:163-197 (inline block) -> "mesh_normalize"
 Not coverable by execution (their arithmetic is inside absent native packages): tiny-cuda-nn hash grid, nvdiffrast
 rasterize / antialias / texture, envlight cubemaps, diffusers UNet / ControlNet / VAE, the `_raytracing` BVH.
 """
@@ -214,6 +216,16 @@ def main():
     G["maps"] = {"depth_png_u16": torch.from_numpy(depth_mm.astype(np.int32)), "rgb_png_u8": {k: torch.from_numpy(v) for k, v in rgb_files.items()},
                  "size": dst_hw, "depth": torch.from_numpy(d_out).float(), "rgb": rgb_out}
 
+    # ------------------------------------------------------------------ env map decoding (a4 input): load_hdr_image on the shipped map1.exr
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    nh = base_ns(); nh["cv2"] = cv2
+    lift("models/materials/dreammat_material.py", ["load_hdr_image"], nh)
+    exr = os.path.join(os.path.dirname(REF), "load/lights/envmap/map1/map1.exr")
+    img = torch.tensor(nh["load_hdr_image"](exr), dtype=torch.float32)            # configure(): torch.tensor(load_hdr_image(pathexr), float32)
+    G["envmap"] = {"relpath": "load/lights/envmap/map1/map1.exr", "shape": tuple(img.shape), "sum": float(img.double().sum()),
+                   "min": float(img.min()), "max": float(img.max()), "crop": img[1000:1016, 2000:2016].clone(),
+                   "rows": img[::256, ::512].clone()}
+
     # ------------------------------------------------------------------ contract_to_unisphere (a3)
     lift("models/geometry/base.py", ["contract_to_unisphere"], ns)
     x = torch.rand(50, 3, generator=g) * 2.4 - 1.2
@@ -373,6 +385,17 @@ def main():
     f = torch.randint(0, 30, (50, 3), generator=g)
     mesh = Fake(v_pos=v, t_pos_idx=f).bind(nv, ["_compute_vertex_normal"])
     G["vertex_normals"] = {"v": v, "f": f, "out": mesh._compute_vertex_normal()}
+
+    # ------------------------------------------------------------------ mesh normalisation block (dreammat_mesh.py:163-197)
+    nmn = base_ns()
+    span = lift_block("models/geometry/dreammat_mesh.py", "centroid = mesh.vertices.mean(0)", "mesh.vertices = np.dot(mesh2std, mesh.vertices.T).T",
+                      nmn, "normalize_block", ["self", "mesh"], "mesh.vertices")
+    verts = np.random.RandomState(7).randn(40, 3) * np.array([1.0, 2.5, 0.7]) + np.array([0.3, -1.0, 2.0])
+    cases_m = []
+    for up, front, sc in (("+z", "+x", 0.8), ("+y", "+z", 0.5), ("-y", "+x", 0.8), ("+x", "-z", 1.0)):
+        me = Fake(cfg=Fake(shape_init_mesh_up=up, shape_init_mesh_front=front, shape_init_params=sc)).bind(nmn, ["normalize_block"])
+        cases_m.append((up, front, sc, torch.from_numpy(me.normalize_block(Fake(vertices=verts.copy())))))
+    G["mesh_normalize"] = {"vertices": torch.from_numpy(verts), "cases": cases_m, "lines": span}
 
     # ------------------------------------------------------------------ feature MLP (a3): module structure + forward
     nn_ = base_ns(); nn_["get_activation"] = ns["get_activation"]
