@@ -5,8 +5,8 @@ import torch
 
 def run():
     from oracle import sd as O
-    from . import weights as Wt
-    from .guidance import PromptProcessorOutput, StableDiffusionLightGuidance, _SDSLoss
+    from dreammat_b200 import weights as Wt
+    from dreammat_b200.guidance import PromptProcessorOutput, StableDiffusionLightGuidance, _SDSLoss
     Q = lambda x: x.half().float()  # noqa: E731
     ucfg = O.UNetConfig(block_out_channels=(64, 128, 128, 128), heads=(1, 2, 2, 2), cross_attention_dim=64)
     vcfg = O.VAEConfig(block_out_channels=(64, 64, 64, 64))

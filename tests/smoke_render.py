@@ -1,13 +1,13 @@
-"""One tiny SDS iteration slice on cuda:0, checked against the CPU oracle (used by
-__graft_entry__.smoke(); the oracle is only the checker here)."""
+"""One tiny SDS iteration slice on cuda:0, checked against the CPU oracle (called by __graft_entry__.smoke(); lives under
+tests/ because it imports the oracle -- nothing in the dreammat_b200 package does)."""
 import torch
 
 
 def run():
     from oracle import render as O
     from tests._fixtures import make_scene, rel_err
-    from . import render_ops as ops
-    from ._cabi import MaterialCfg
+    from dreammat_b200 import render_ops as ops
+    from dreammat_b200._cabi import MaterialCfg
     sc = make_scene(res=32, subdiv=2, bump=0.1, seed=1)
     dev = "cuda:0"
     torch.cuda.set_device(0)
@@ -46,8 +46,5 @@ def run():
     e2 = rel_err(gc.grad.cpu(), gp.grad)
     print(f"smoke: rgb rel err {e1:.2e}, hash-grid grad rel err {e2:.2e}, pn={sc['pn']}")
     assert e1 < 1e-3 and e2 < 5e-3, (e1, e2)
-    try:
-        from . import dense_smoke
-        dense_smoke.run()
-    except ImportError:
-        pass
+    from tests import smoke_dense
+    smoke_dense.run()
