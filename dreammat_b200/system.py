@@ -401,7 +401,10 @@ class DreamMat:
             from .parallel import exchange_rows, pixel_partition
             gvid = [int(v) for v in batch["global_view_id"]]
             geid = [int(e) for e in batch["global_env_id"]]
-            segments, counts = pixel_partition([ren._cache[v]["pn"] for v in gvid], self.world_size)
+            pn_global = [ren._cache[v]["pn"] for v in gvid]
+            if total_pn_global is None:
+                total_pn = sum(pn_global)          # the global pixel count is known locally: every rank caches every view
+            segments, counts = pixel_partition(pn_global, self.world_size)
             my_segs = [(ren._cache[gvid[g]], geid[g], a, bb, g) for (g, a, bb) in segments[self.rank]]
             send_counts = counts[self.rank]
             recv_counts = [counts[r][self.rank] for r in range(self.world_size)]
