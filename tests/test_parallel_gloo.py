@@ -145,3 +145,84 @@ def test_exchange_rows_roundtrip_gloo():
     port = _free_port()
     mp.spawn(_a2a_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)), dict(ret)
+
+
+def _balanced_worker(rank, world, port, ret):
+    """Pixel-balanced step with the CPU oracle as the per-pixel compute: every rank shades an equal interval of the global
+    pixel line, colours travel to the view owners (all-to-all), d loss / d colour travels back (transposed all-to-all), the
+    parameter gradients meet in the all-reduce.  Must equal the single-process gradient."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from dreammat_b200.parallel import allreduce_gradients, exchange_rows, pixel_partition
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    V = 4
+    sc = make_scene(res=16, subdiv=2, bump=0.1, seed=0, n_views=V)
+    meta, total = OR.hashgrid_meta(log2_T=10)
+    n_grid = total * 2
+    g = torch.Generator().manual_seed(0)
+    P0 = torch.cat([(torch.rand(n_grid, generator=g) * 2 - 1) * 0.3, (torch.rand(2048, generator=g) * 2 - 1) / 5.6,
+                    (torch.rand(320, generator=g) * 2 - 1) / 8])
+    env = OR.synthetic_envmap(32, 64, 0)
+    pn = [int(sc["gb"]["selector"][b].sum()) for b in range(V)]
+    total_pn = sum(pn)
+    per = V // world
+    segs, counts = pixel_partition(pn, world)
+    recv_counts = [counts[r][rank] for r in range(world)]
+
+    def view_arrays(b):
+        sel = sc["gb"]["selector"][b]
+        gg = torch.Generator().manual_seed(100 + b)          # per-pixel draws are a function of the view only
+        n = pn[b]
+        return (sc["gb"]["gb_pos"][b][sel], sc["gb"]["gb_normal"][b][sel], sc["gb"]["gb_viewdirs"][b][sel], torch.rand(n, 1, generator=gg),
+                torch.randn(n, 1, generator=gg) * 0.05, torch.rand(n, 1, 1, generator=gg), torch.rand(n, 1, 1, generator=gg))
+
+    def shade(P, b, a, bb):
+        grid, W1, W2 = P[:n_grid], P[n_grid:n_grid + 2048].view(64, 32), P[n_grid + 2048:].view(5, 64)
+        pts, nrm, vd, ang, eps, rd, rs = (t[a:bb] for t in view_arrays(b))
+        f = OR.geometry_forward(pts, grid, W1, W2, meta)
+        fj = OR.geometry_forward(OR.jitter_positions(pts, nrm, ang, eps), grid, W1, W2, meta)
+        al, me, ro, _ = OR.material_params(f, fj)
+        o = OR.shade_raytracing(pts, nrm, vd, env, me, ro, al, rd, rs, lambda oo, dd: sc["tracer"].trace(oo, dd)[1], n_diffuse=16, n_specular=8)
+        m, mj = torch.sigmoid(f), torch.sigmoid(fj)
+        kd, ks = (m[:, :3] - mj[:, :3]).abs(), (m[:, 3:5] - mj[:, 3:5]).abs()
+        reg = (0.25 * (kd.mean(-1) * kd[:, 2]).sum() + 0.1 * (ks[:, 0] * ks[:, 1]).sum()) / total_pn
+        return o["color"], reg
+
+    def view_loss(color):          # stands in for the SDS term: any function of a view's whole image
+        return 0.5 * ((color - 0.3) ** 2).sum() * (1.0 / V) + 0.01 * color.mean() * color.std()
+
+    # ---- balanced, distributed
+    P = P0.clone().requires_grad_(True)
+    cols, regs = zip(*[shade(P, gv, a, bb) for (gv, a, bb) in segs[rank]])
+    color_sh = torch.cat(cols)
+    own = exchange_rows(color_sh.detach(), counts[rank], recv_counts, world).requires_grad_(True)
+    off, loss_own = 0, 0.0
+    for b in range(rank * per, (rank + 1) * per):
+        loss_own = loss_own + view_loss(own[off:off + pn[b]]); off += pn[b]
+    assert off == own.shape[0]
+    (dcol_own,) = torch.autograd.grad(loss_own, own)
+    dcol_sh = exchange_rows(dcol_own, recv_counts, counts[rank], world)
+    ((color_sh * dcol_sh).sum() + sum(regs)).backward()
+    flat = P.grad.clone()
+    allreduce_gradients(flat, world)
+    if rank == 0:
+        Ps = P0.clone().requires_grad_(True)
+        full = 0.0
+        for b in range(V):
+            c, r_ = shade(Ps, b, 0, pn[b])
+            full = full + view_loss(c) + r_
+        full.backward()
+        ret["err"] = float((flat - Ps.grad).norm() / Ps.grad.norm())
+        ret["imbalance"] = max(sum(bb - a for (_, a, bb) in s) for s in segs) - min(sum(bb - a for (_, a, bb) in s) for s in segs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pixel_balanced_gradient_equals_single_process():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_balanced_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["imbalance"] <= 1
+    assert ret["err"] < 1e-5, ret["err"]
