@@ -264,6 +264,14 @@ class StableDiffusionLightGuidance:
             vae_eps = torch.randn(B, 4, H // 8, W // 8, device=self.device)     # posterior.sample() (appendix B #7)
         return _VAEEncode.apply(rgb_bhwc.contiguous(), self.vae, vae_eps, self.weights_dtype)
 
+    @staticmethod
+    def _cond_to_latent_grid(cond_bhwc, h, w):
+        """prepare_image_cond (dreammat_guidance.py:518-534): a condition map that is not at the VAE input size (8 x the
+        latent grid, 512^2 for SD) is resized with F.interpolate(..., mode="bilinear", align_corners=False)."""
+        if cond_bhwc.shape[1] != 8 * h or cond_bhwc.shape[2] != 8 * w:
+            return R.resize_bilinear(cond_bhwc, 8 * h, 8 * w)
+        return cond_bhwc
+
     @torch.no_grad()
     def predict_noise(self, latents, t, noise, ctx3, cond_bhwc, condition_scale):
         """compute_without_perpneg (:388-438): 3-branch batch [text | uncond | null] -> eps [3,B,4,h,w] fp32."""
@@ -274,7 +282,8 @@ class StableDiffusionLightGuidance:
         ctx = ctx3.to(self.device, self.weights_dtype).contiguous()
         down = mid = None
         if self.use_controlnet and condition_scale != 0:
-            cond = D.pad_convert(cond_bhwc, 64, 1.0, 0.0, self.weights_dtype)
+            cond = D.pad_convert(self._cond_to_latent_grid(cond_bhwc, latents.shape[-2], latents.shape[-1]), 64, 1.0, 0.0,
+                                 self.weights_dtype)
             down, mid = self.controlnet.forward(zt, t3, ctx, cond, float(condition_scale))
         eps = self.unet.forward(zt, t3, ctx, down, mid)
         return eps.view(3, B, *eps.shape[1:])
@@ -323,7 +332,7 @@ class StableDiffusionLightGuidance:
         ac = self.alphas[t]
         g.sqrt_ac.copy_(ac.sqrt()); g.sqrt_1mac.copy_((1 - ac).sqrt()); g.t3.copy_(torch.cat([t] * 3).float())
         g.ctx.copy_(ctx3)
-        g.cond.copy_(cond_bhwc)
+        g.cond.copy_(self._cond_to_latent_grid(cond_bhwc, g.noise.shape[-2], g.noise.shape[-1]))
         g.g_unet.replay()
         if mark:
             mark("unet_cn")
