@@ -42,6 +42,7 @@ SIGNATURES = {
     "dm_launch_count": (C.c_longlong, []),
     "dm_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "dm_tune_gemm": (C.c_int, [C.c_int]),
+    "dm_gemm_plan": (C.c_int, [I64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dm_gemm_workspace_bytes": (C.c_size_t, []),
     "dm_gemm_set_workspace": (C.c_int, [P, C.c_size_t]),
     "dm_tune_attention": (C.c_int, [C.c_int]),

@@ -986,6 +986,30 @@ int dispatch_halo(const CUtensorMap& tmH, const CUtensorMap& tmB, const GemmPara
 
 }  // namespace
 
+// Pure query of the tile heuristic (no launch): which kernel / tile width / split-K a [M, N, K] contraction would get.
+// kernel_out: 0 single-CTA, 1 CTA pair.  split_out is the pair path's request, or for the single-CTA path what
+// pick_split would choose given a registered workspace.  Lets host-side tests pin the measured choices.
+extern "C" int dm_gemm_plan(int64_t M, int N, int K, int act, int bn_hint, int* kernel_out, int* bn_out, int* split_out) {
+    DM_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0 && kernel_out && bn_out && split_out, "bad args");
+    TileChoice tc = choose_tile(M, N, K / BK, bn_hint, act);
+    *kernel_out = tc.pair ? 1 : 0;
+    *bn_out = tc.bn;
+    int split = tc.split > 1 ? tc.split : 1;
+    if (!tc.pair && tc.split == 0) {
+        const int64_t tiles = dm_ceil_div(N, tc.bn) * dm_ceil_div(M, BM);
+        const int nk = K / BK;
+        if (g_gemm_splitk && act != 3 && (N & 3) == 0 && tiles * 2 <= DM_NUM_SMS && nk >= 32 && g_ws != nullptr &&
+            (size_t)(M * N) <= g_ws_floats) {
+            int s2 = (int)(DM_NUM_SMS / tiles);
+            if (s2 > nk / 8) s2 = nk / 8;
+            if (s2 > 16) s2 = 16;
+            if (s2 >= 2) split = s2;
+        }
+    }
+    *split_out = split;
+    return DM_OK;
+}
+
 extern "C" size_t dm_gemm_workspace_bytes(void) { return WS_FLOATS * sizeof(float); }
 
 extern "C" int dm_gemm_set_workspace(void* ptr, size_t bytes) {

@@ -36,6 +36,8 @@ int dm_tune_attention(int mode);       /* softmax variant: 0 fp32 exponentials, 
                                       * 1 packed f16x2 exponentials + lazy rescale; 2 fp32 + lazy rescale */
 /* split-K scratch: a caller-owned, ZERO-FILLED device buffer of fp32 partial sums (the finish kernel re-zeroes what it
  * reads, so it stays zero between calls).  Without a workspace split-K is not used.  One per process / device. */
+/* pure query of the measured tile heuristic: kernel (0 single CTA, 1 CTA pair), tile width, split-K factor */
+int dm_gemm_plan(int64_t M, int N, int K, int act, int bn_hint, int* kernel_out, int* bn_out, int* split_out);
 size_t dm_gemm_workspace_bytes(void);
 int dm_gemm_set_workspace(void* device_ptr, size_t bytes);
 int dm_tune_gemm(int code);          /* 1|2: persistent CTAs per SM of the single-CTA kernel (tiles <= 128 wide);
