@@ -131,6 +131,8 @@ def test_gemm_tile_plan_matches_measured_choices():
     """dm_gemm_plan is a pure query of choose_tile(): the kernel / tile width / split-K per layer shape that the sweeps in
     profiles/r01_tile_sweep.txt and r01_exp_splitk.txt selected (8-view batch = 24 UNet samples, one-view batch = 3)."""
     import ctypes as C
+    import __graft_entry__ as g
+    g.build()                                   # no-op when the library is up to date
     from dreammat_b200._cabi import lib
     L = lib()
 
