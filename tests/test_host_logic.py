@@ -156,3 +156,33 @@ def test_gemm_tile_plan_matches_measured_choices():
     finally:
         L.dm_gemm_set_workspace(None, 0)
     assert plan(192, 1280, 11520)[2] == 1                          # no caller-owned workspace -> no split-K
+
+
+def test_weight_layouts_for_the_tensor_core_kernels():
+    """Host-side weight preparation (pure torch, no GPU): the implicit-GEMM K order and the GEGLU row interleave must
+    express the same linear maps as the diffusers layouts."""
+    import torch.nn.functional as F
+    from dreammat_b200 import dense_ops as D
+    g = torch.Generator().manual_seed(0)
+    # conv [Cout, Cin, 3, 3] -> [Cout, 9 * Cin_pad], K index = tap * Cin_pad + c with tap = kh * 3 + kw
+    w = torch.randn(6, 5, 3, 3, generator=g)
+    wg = D.conv_weight_to_gemm(w, cin_pad=8, cout_pad=0, dtype=torch.float32)
+    assert wg.shape == (6, 72)
+    x = torch.randn(2, 5, 7, 7, generator=g)
+    xp = F.pad(x, (1, 1, 1, 1))
+    cols = torch.zeros(2, 7, 7, 72)
+    for kh in range(3):
+        for kw in range(3):
+            cols[..., (kh * 3 + kw) * 8:(kh * 3 + kw) * 8 + 5] = xp[:, :, kh:kh + 7, kw:kw + 7].permute(0, 2, 3, 1)
+    assert torch.allclose(cols @ wg.t(), F.conv2d(x, w, padding=1).permute(0, 2, 3, 1), atol=1e-5)
+    # GEGLU: diffusers computes hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate).  The fused epilogue reads the
+    # projection in blocks of 64 columns = [32 value | 32 gate]
+    Dh = 96
+    wp, bp = torch.randn(2 * Dh, 16, generator=g), torch.randn(2 * Dh, generator=g)
+    a = torch.randn(10, 16, generator=g)
+    pr = a @ wp.t() + bp
+    want = pr[:, :Dh] * F.gelu(pr[:, Dh:])
+    pi = a @ D.geglu_interleave(wp).t() + D.geglu_interleave(bp)
+    blk = pi.view(10, Dh // 32, 2, 32)
+    got = (blk[:, :, 0] * F.gelu(blk[:, :, 1])).reshape(10, Dh)
+    assert torch.allclose(got, want, atol=1e-6)
