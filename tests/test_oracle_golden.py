@@ -149,6 +149,8 @@ def test_material_forward_backward_and_export(G):
     g = G["material"]
     gi, go = g["in"], g["out"]
     assert close(OR.direction_tables(gi["n_diffuse"]), gi["tab_d"]) and close(OR.direction_tables(gi["n_specular"]), gi["tab_s"])
+    from dreammat_b200 import render_ops as R          # the tables the CUDA shader is fed (host side, numpy)
+    assert close(R.direction_tables(gi["n_diffuse"]), gi["tab_d"]) and close(R.direction_tables(gi["n_specular"]), gi["tab_s"])
     f = gi["features"].clone().requires_grad_(True)
     fj = gi["features_jitter"].clone().requires_grad_(True)
     al, me, ro, reg = OR.material_params(f, fj)
