@@ -48,6 +48,12 @@ def test_collate_cameras_rays_and_draws(G):
                         torch.Generator().manual_seed(0))
     v2, e2 = cams.collate(torch.Generator().manual_seed(gi["seed"]), B)
     assert torch.equal(v2, go["view_id"]) and torch.equal(e2, go["env_id"])
+    # ... and builds the same cameras / rays / matrices for them (scene.FixCameraSet.cameras = uncond.py:740-796)
+    cams.elevation_deg, cams.azimuth_deg = gi["elevation_degs"], gi["azimuth_degs"]
+    cams.camera_distances, cams.fovy_deg = gi["fix_camera_distances"], gi["fovy_degs"]
+    pc = cams.cameras(v2)
+    for k in ("rays_o", "rays_d", "mvp_mtx", "c2w", "w2c", "camera_positions", "elevation", "azimuth", "camera_distances"):
+        assert close(pc[k], go[k]), k
 
 
 def test_fixed_view_set_draw_order(G):
