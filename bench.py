@@ -264,7 +264,10 @@ def run_ours(args):
         ach = DENSE_TFLOP_PER_VIEW * Vl / (t_dense / 1000.0)
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
                            "traffic": None, "kernel": "tc_gemm_pair_kernel + tc_gemm_kernel + attention_kernel over the dense section",
-                           "peak_source": src + " sustained bf16"}
+                           "peak_source": src + " sustained bf16",
+                           "note": "section-level: algorithmic flops of ALL dense kernels / CUDA-event time of the section inside the timed "
+                                   "step (GroupNorm, softmax etc. included); the dominant tensor kernel alone is in roofline_kernel, the "
+                                   "MC shader (45 % of the step, issue-bound) in roofline_shading"}
         out["sections_ms"] = sec
         try:
             out["roofline_kernel"] = kernel_roofline(dtype)
