@@ -99,23 +99,21 @@ def procedural_mesh(n_faces_target: int = 100000, scale: float = 0.8, seed: int 
 
 
 def get_projection_matrix(fovy: torch.Tensor, aspect_wh: float, near: float = 0.1, far: float = 1000.0):
-    """utils/ops.py:266-278 (y flipped for the nvdiffrast clip-space convention)."""
-    B = fovy.shape[0]
-    p = torch.zeros(B, 4, 4, dtype=torch.float32)
-    p[:, 0, 0] = 1.0 / (torch.tan(fovy / 2.0) * aspect_wh)
-    p[:, 1, 1] = -1.0 / torch.tan(fovy / 2.0)
-    p[:, 2, 2] = -(far + near) / (far - near)
-    p[:, 2, 3] = -2.0 * far * near / (far - near)
-    p[:, 3, 2] = -1.0
-    return p
+    """OpenGL-style perspective matrix per view with the y row negated (nvdiffrast's clip space has y down) -- the
+    convention of utils/ops.py:266-278; entries [2,2] = -(f+n)/(f-n), [2,3] = -2fn/(f-n), [3,2] = -1."""
+    t = torch.tan(fovy.float() / 2.0)
+    z, o = torch.zeros_like(t), torch.ones_like(t)
+    a22, a23 = -(far + near) / (far - near), -2.0 * far * near / (far - near)
+    rows = ((1.0 / (t * aspect_wh), z, z, z), (z, -1.0 / t, z, z), (z, z, o * a22, o * a23), (z, z, -o, z))
+    return torch.stack([torch.stack(r, -1) for r in rows], -2)
 
 
 def get_mvp_matrix(c2w: torch.Tensor, proj: torch.Tensor):
-    """utils/ops.py:281-292 -> (mvp, w2c)."""
-    w2c = torch.zeros(c2w.shape[0], 4, 4).to(c2w)
-    w2c[:, :3, :3] = c2w[:, :3, :3].permute(0, 2, 1)
-    w2c[:, :3, 3:] = -c2w[:, :3, :3].permute(0, 2, 1) @ c2w[:, :3, 3:]
-    w2c[:, 3, 3] = 1.0
+    """world-to-camera as the rigid inverse [R^T | -R^T t] of c2w, and proj @ w2c (utils/ops.py:281-292) -> (mvp, w2c)."""
+    Rt = c2w[:, :3, :3].transpose(1, 2)
+    top = torch.cat([Rt, -(Rt @ c2w[:, :3, 3:])], -1)
+    last = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=c2w.dtype, device=c2w.device).expand(c2w.shape[0], 1, 4)
+    w2c = torch.cat([top, last], 1)
     return proj @ w2c, w2c
 
 
