@@ -150,7 +150,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is left exactly as the launcher set it (its banner goes to stderr with everything else, see main())
         dist.init_process_group("nccl", device_id=torch.device(device))
     from dreammat_b200 import _cabi
     _cabi.check(_cabi.lib().dm_device_check(local), "dm_device_check")   # fails loudly without the sm_100a library
@@ -164,7 +164,8 @@ def run_ours(args):
     sysm.world_size, sysm.rank = world, rank
     sysm.balance_pixels = not args.no_balance
     if not args.no_graphs:
-        sysm.guidance.enable_graphs(Vl, args.res, args.res)     # dense section as three captured CUDA graphs
+        gres = 512 if sysm.resize_to_vae else args.res          # renders that are not 512^2 are resized before the VAE
+        sysm.guidance.enable_graphs(Vl, gres, gres)              # dense section as three captured CUDA graphs
     res = args.res
     # a1: per-view camera tensors (fixed set) resident on the device; G-buffers produced once per fixed view
     all_ids = torch.arange(cams.cfg.fix_view_num)
@@ -176,6 +177,7 @@ def run_ours(args):
             sysm.renderer.gbuffer(one["rays_o"], one["rays_d"], one["mvp_mtx"], one["w2c"], v0 + j)
             cam_dev.append({k: one[k] for k in ("mvp_mtx", "w2c", "elevation", "azimuth", "camera_distances")})
     pn = [sysm.renderer._cache[i]["pn"] for i in range(cams.cfg.fix_view_num)]
+    sysm.prepare_balanced(range(cams.cfg.fix_view_num))          # one MIN all-reduce: all ranks agree on balanced shading
     # condition maps: synthetic pool standing in for the Blender pre-renders (depth1 + normal3 + 6 x RGB light)
     POOL = 16
     gcond = torch.Generator().manual_seed(7)

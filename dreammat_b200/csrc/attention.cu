@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "dense_hp.cuh"
 
 namespace {
 
@@ -364,6 +365,10 @@ extern "C" int dm_attention(int bf16, const void* q, int64_t ldq, int64_t q_batc
                             int batch, int heads, int Nq, int Nk, int head_dim, float scale, void* stream) {
     DM_REQUIRE(q && k && v && out, "null pointer");
     DM_REQUIRE(head_dim == HD, "head_dim 64 only (VAE mid-block attention uses the GEMM path)");
+    DM_REQUIRE(bf16 >= 0 && bf16 <= 2, "dtype selector: 0 fp16, 1 bf16, 2 fp32");
+    if (bf16 == 2)   // fp32 storage (high-precision mode): SIMT online-softmax kernel of dense_hp.cu
+        return hp_attention((const float*)q, ldq, q_batch_stride, (const float*)k, (const float*)v, ldkv, kv_batch_stride,
+                            (float*)out, ldo, out_batch_stride, batch, heads, Nq, Nk, scale, stream);
     DM_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "row strides must be multiples of 8 elements");
     DM_REQUIRE(Nq > 0 && Nk > 0 && batch > 0 && heads > 0, "sizes");
     CUtensorMap tq, tk, tv;

@@ -11,6 +11,7 @@
 // DDIMScheduler.add_noise (:463), Timesteps / get_timestep_embedding.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "dense_hp.cuh"
 
 namespace {
 
@@ -24,11 +25,25 @@ template <> struct H<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat16 t(float v) { return __float2bfloat16_rn(v); }
 };
 
+template <> struct H<float> {
+    static __device__ __forceinline__ float f(float v) { return v; }
+    static __device__ __forceinline__ float t(float v) { return v; }
+};
+
+// storage dtype selector of every dense-path entry point: 0 fp16, 1 bf16, 2 fp32 (high-precision mode, dense_hp.cu)
 #define DM_DISPATCH_T(bf16, ...)                                  \
     do {                                                          \
         if (bf16) { using T = __nv_bfloat16; __VA_ARGS__; }       \
         else { using T = __half; __VA_ARGS__; }                   \
     } while (0)
+// element-wise kernels (no 16-bit vector packing) also run on fp32 storage
+#define DM_DISPATCH_T3(dt, ...)                                   \
+    do {                                                          \
+        if ((dt) == 2) { using T = float; __VA_ARGS__; }          \
+        else if (dt) { using T = __nv_bfloat16; __VA_ARGS__; }    \
+        else { using T = __half; __VA_ARGS__; }                   \
+    } while (0)
+#define DM_DTYPE_OK(dt) DM_REQUIRE((dt) >= 0 && (dt) <= 2, "dtype selector: 0 fp16, 1 bf16, 2 fp32")
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float silu_grad(float x) {
@@ -604,6 +619,8 @@ inline int gn_chunks(int n_img, int HW, int slabs, int lanes) {
 
 extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, int ld, int G, const void* gamma,
                             const void* beta, float eps, int silu, void* y, int ldy, float* stats, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_groupnorm((const float*)x, n_img, HW, C, ld, G, (const float*)gamma, (const float*)beta, eps, silu, (float*)y, ldy, stats, stream);
     DM_REQUIRE(x && gamma && beta && y && stats, "null pointer");
     DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0 && ld % 8 == 0 && ldy % 8 == 0, "channel layout");
     cudaStream_t st = (cudaStream_t)stream;
@@ -622,6 +639,8 @@ extern "C" int dm_groupnorm(int bf16, const void* x, int n_img, int HW, int C, i
 extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_img, int HW, int C, int G,
                                 const void* gamma, const void* beta, float eps, int silu, const float* stats,
                                 float* bstats, const void* dx_add, void* dx, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_groupnorm_bwd((const float*)x, (const float*)dz, n_img, HW, C, G, (const float*)gamma, (const float*)beta, eps, silu, stats, (const float*)dx_add, (float*)dx, stream);
     DM_REQUIRE(x && dz && gamma && beta && stats && bstats && dx, "null pointer");
     DM_REQUIRE(C % 8 == 0 && C % G == 0 && (C / G) % 2 == 0, "channel layout");
     cudaStream_t st = (cudaStream_t)stream;
@@ -640,6 +659,8 @@ extern "C" int dm_groupnorm_bwd(int bf16, const void* x, const void* dz, int n_i
 
 extern "C" int dm_layernorm(int bf16, const void* x, int64_t M, int C, const void* gamma, const void* beta, float eps,
                             void* y, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_layernorm((const float*)x, M, C, (const float*)gamma, (const float*)beta, eps, (float*)y, stream);
     DM_REQUIRE(x && gamma && beta && y, "null pointer");
     DM_REQUIRE(C <= 1280 && C % 8 == 0, "C <= 1280, multiple of 8");
     if (M == 0) return DM_OK;
@@ -650,6 +671,8 @@ extern "C" int dm_layernorm(int bf16, const void* x, int64_t M, int C, const voi
 }
 
 extern "C" int dm_geglu(int bf16, const void* h, int64_t M, int D, void* out, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_geglu((const float*)h, M, D, (float*)out, stream);
     DM_REQUIRE(h && out && D % 8 == 0, "bad args");
     DM_DISPATCH_T(bf16, geglu_kernel<T><<<grid_for(M * (D / 8)), 256, 0, (cudaStream_t)stream>>>((const T*)h, M, D, (T*)out));
     DM_CHECK_LAUNCH();
@@ -657,6 +680,8 @@ extern "C" int dm_geglu(int bf16, const void* h, int64_t M, int D, void* out, vo
 }
 
 extern "C" int dm_upsample2x(int bf16, const void* x, int n, int H, int W, int C, int zero_insert, void* y, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return dm_upsample2x(0, x, n, H, W, 2 * C, zero_insert, y, stream);
     DM_REQUIRE(x && y && C % 8 == 0, "bad args");
     int64_t nv = (int64_t)n * 4 * H * W * (C / 8);
     if (zero_insert) DM_DISPATCH_T(bf16, zero_insert2x_kernel<T><<<grid_for(nv), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, H, W, C, (T*)y));
@@ -667,6 +692,8 @@ extern "C" int dm_upsample2x(int bf16, const void* x, int n, int H, int W, int C
 
 extern "C" int dm_axpby2d(int bf16, const void* s1, int64_t ld1, float a, const void* s2, int64_t ld2, float b,
                           int64_t rows, int cols, void* dst, int64_t ldd, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_axpby2d((const float*)s1, ld1, a, (const float*)s2, ld2, b, rows, cols, (float*)dst, ldd, stream);
     DM_REQUIRE(s1 && dst && cols % 8 == 0 && ld1 % 8 == 0 && ldd % 8 == 0 && (!s2 || ld2 % 8 == 0), "bad args");
     if (rows == 0) return DM_OK;
     DM_DISPATCH_T(bf16, axpby2d_kernel<T><<<grid_for(rows * (cols / 8)), 256, 0, (cudaStream_t)stream>>>((const T*)s1, ld1, a, (const T*)s2, ld2, b,
@@ -677,6 +704,8 @@ extern "C" int dm_axpby2d(int bf16, const void* s1, int64_t ld1, float a, const 
 
 extern "C" int dm_transpose(int bf16, const void* x, int batch, int R, int C, int64_t ldx, int64_t bsx, void* y,
                             int64_t ldy, int64_t bsy, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_transpose((const float*)x, batch, R, C, ldx, bsx, (float*)y, ldy, bsy, stream);
     DM_REQUIRE(x && y, "null pointer");
     DM_REQUIRE(((R | C) & 1) == 0 && ((ldx | ldy | bsx | bsy) & 1) == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 3) == 0,
                "transpose moves 32-bit pairs: even extents / strides, 4-byte aligned bases");
@@ -688,24 +717,28 @@ extern "C" int dm_transpose(int bf16, const void* x, int batch, int R, int C, in
 
 extern "C" int dm_softmax_rows(int bf16, const void* x, int64_t rows, int cols, int64_t ld, float scale, void* y,
                                void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(x && y, "null pointer");
     if (rows == 0) return DM_OK;
-    DM_DISPATCH_T(bf16, softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, cols, ld, scale, (T*)y));
+    DM_DISPATCH_T3(bf16, softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, cols, ld, scale, (T*)y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_softmax_bwd(int bf16, const void* P, const void* dP, int64_t rows, int cols, int64_t ld, float scale,
                               void* dS, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(P && dP && dS, "null pointer");
     if (rows == 0) return DM_OK;
-    DM_DISPATCH_T(bf16, softmax_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)P, (const T*)dP, cols, ld, scale, (T*)dS));
+    DM_DISPATCH_T3(bf16, softmax_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)P, (const T*)dP, cols, ld, scale, (T*)dS));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, int cpad, float scale, float shift,
                               void* y, void* stream) {
+    DM_DTYPE_OK(bf16);
+    if (bf16 == 2) return hp_pad_convert(x, rows, cin, cpad, scale, shift, (float*)y, stream);
     DM_REQUIRE(x && y && cpad >= cin && cpad % 8 == 0, "bad args (cpad must be a multiple of 8)");
     DM_DISPATCH_T(bf16, pad_convert_kernel<T><<<grid_for(rows * (cpad / 8)), 256, 0, (cudaStream_t)stream>>>(x, rows, cin, cpad, scale, shift, (T*)y));
     DM_CHECK_LAUNCH();
@@ -714,31 +747,35 @@ extern "C" int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, i
 
 extern "C" int dm_unpad_convert(int bf16, const void* x, int64_t rows, int ld, int cout, float scale, float* y,
                                 void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(x && y && ld >= cout, "bad args");
-    DM_DISPATCH_T(bf16, unpad_convert_kernel<T><<<grid_for(rows * cout), 256, 0, (cudaStream_t)stream>>>((const T*)x, rows, ld, cout, scale, y));
+    DM_DISPATCH_T3(bf16, unpad_convert_kernel<T><<<grid_for(rows * cout), 256, 0, (cudaStream_t)stream>>>((const T*)x, rows, ld, cout, scale, y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_nhwc_to_nchw_f32(int bf16, const void* x, int n, int HW, int ld, int C, float* y, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(x && y, "null pointer");
-    DM_DISPATCH_T(bf16, nhwc_to_nchw_f32_kernel<T><<<grid_for((int64_t)n * C * HW), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, HW, ld, C, y));
+    DM_DISPATCH_T3(bf16, nhwc_to_nchw_f32_kernel<T><<<grid_for((int64_t)n * C * HW), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, HW, ld, C, y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_vae_sample(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling,
                              float* z, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(moments && eps && z && ld >= 8, "bad args");
-    DM_DISPATCH_T(bf16, vae_sample_kernel<T><<<grid_for((int64_t)n * 4 * HW), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps, scaling, z));
+    DM_DISPATCH_T3(bf16, vae_sample_kernel<T><<<grid_for((int64_t)n * 4 * HW), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps, scaling, z));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_vae_sample_bwd(int bf16, const void* moments, int n, int HW, int ld, const float* eps, float scaling,
                                  const float* dz, void* dmoments, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(moments && eps && dz && dmoments && ld >= 8, "bad args");
-    DM_DISPATCH_T(bf16, vae_sample_bwd_kernel<T><<<grid_for((int64_t)n * HW * ld), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps,
+    DM_DISPATCH_T3(bf16, vae_sample_bwd_kernel<T><<<grid_for((int64_t)n * HW * ld), 256, 0, (cudaStream_t)stream>>>((const T*)moments, n, HW, ld, eps,
                                                                                                                scaling, dz, (T*)dmoments));
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -746,23 +783,26 @@ extern "C" int dm_vae_sample_bwd(int bf16, const void* moments, int n, int HW, i
 
 extern "C" int dm_add_noise(int bf16, const float* z, const float* noise, const float* sqrt_ac, const float* sqrt_1mac,
                             int B, int HW, int cpad, int rep, void* out, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(z && noise && sqrt_ac && sqrt_1mac && out && cpad >= 4, "bad args");
-    DM_DISPATCH_T(bf16, add_noise_kernel<T><<<grid_for((int64_t)rep * B * HW * cpad), 256, 0, (cudaStream_t)stream>>>(z, noise, sqrt_ac, sqrt_1mac, B, HW,
+    DM_DISPATCH_T3(bf16, add_noise_kernel<T><<<grid_for((int64_t)rep * B * HW * cpad), 256, 0, (cudaStream_t)stream>>>(z, noise, sqrt_ac, sqrt_1mac, B, HW,
                                                                                                                   cpad, rep, (T*)out));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_timestep_embedding(int bf16, const float* t, int n, int dim, void* out, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(t && out && dim % 2 == 0, "bad args");
-    DM_DISPATCH_T(bf16, timestep_embed_kernel<T><<<(unsigned)dm_ceil_div((int64_t)n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, n, dim, (T*)out));
+    DM_DISPATCH_T3(bf16, timestep_embed_kernel<T><<<(unsigned)dm_ceil_div((int64_t)n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, n, dim, (T*)out));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }
 
 extern "C" int dm_silu(int bf16, const void* x, int64_t n, void* y, void* stream) {
+    DM_DTYPE_OK(bf16);
     DM_REQUIRE(x && y, "null pointer");
-    DM_DISPATCH_T(bf16, silu_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, (T*)y));
+    DM_DISPATCH_T3(bf16, silu_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, (T*)y));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

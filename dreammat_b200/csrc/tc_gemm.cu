@@ -52,7 +52,20 @@ struct GemmParams {
     float out_scale;                        // applied last
     int act;                                // 0 none, 1 silu, 2 gelu(erf), 3 geglu (interleaved value|gate)
     int split_k; float* ws;                 // split-K: fp32 partial sums are red.add'ed into ws[M, N]; splitk_finish_kernel applies the epilogue
+    // fused CSD epilogue of the UNet's conv_out (dm_conv2d_csd): rows are [branch][view][pixel]; a CTA walks the three
+    // branch tiles of the same 128 pixels back to back and combines them in registers
+    int csd; int csd_B; int csd_hw; int csd_groups;       // csd_groups = B*hw / 128 row tiles per branch
+    const float* csd_noise; const float* csd_w; const float* csd_coef;   // coef[5] = c_text, c_uncond, c_null, c_noise, dlat_scale (device)
+    float* csd_grad; float* csd_dlat; float* csd_norms; float* csd_eps;
 };
+
+// i-th tile of this CTA (persistent walk); -1 past the end.  Plain mode: t = first + i * step.  CSD mode: the walk
+// visits GROUPS of three row tiles (k * groups + g, k = branch) so that one CTA sees all three noise predictions of a pixel.
+__device__ __forceinline__ int tile_at(const GemmParams& p, int i, int first, int step, int total_tiles) {
+    if (!p.csd) { const int t = first + i * step; return t < total_tiles ? t : -1; }
+    const int g = first + (i / 3) * step;
+    return g < p.csd_groups ? (i % 3) * p.csd_groups + g : -1;
+}
 
 template <typename T> struct Cvt;
 template <> struct Cvt<__half> {
@@ -226,6 +239,62 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     }
 }
 
+// CSD epilogue (dreammat_guidance.py:475-481 compute_grad_sds tail, :584 nan_to_num, the 8 logged norms of :483-495 and
+// loss_sds of :590-594) on the accumulator tile of branch k = 0 text | 1 uncond | 2 null.  The thread's row is pixel
+// r = g*128 + row of the [view][pixel] axis; its 4 noise predictions (rounded to the storage dtype like the reference's
+// `.sample` in weights_dtype) wait in `e` until the third branch arrives, then
+//   grad = nan_to_num(w[b] * (c_t e_text + c_u e_uncond + c_n e_null + c_s noise)),  dlatents = grad * dlat_scale
+// are written (NCHW fp32) and the ten squared sums are reduced per warp and added to norms[10].
+template <int BN, typename T>
+__device__ __forceinline__ void epilogue_csd(const GemmParams& p, uint32_t tmem_acc, int64_t m, int lane, uint32_t release_bar,
+                                             float (&e)[2][4]) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_acc, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+    const int64_t per_branch = (int64_t)p.csd_groups * BM;
+    const int k = (int)(m / per_branch);
+    const int64_t r = m - (int64_t)k * per_branch;
+    const int b = (int)(r / p.csd_hw), px = (int)(r - (int64_t)b * p.csd_hw);
+    const T* bias = (const T*)p.bias;
+    float cur[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float f = __uint_as_float(v[c]);
+        if (bias) f += Cvt<T>::to_f(bias[c]);
+        cur[c] = Cvt<T>::to_f(Cvt<T>::from_f(f));
+        if (p.csd_eps) p.csd_eps[(((int64_t)k * p.csd_B + b) * 4 + c) * p.csd_hw + px] = cur[c];
+    }
+    if (k < 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[k][c] = cur[c];
+        return;
+    }
+    const float ct = p.csd_coef[0], cu = p.csd_coef[1], cn = p.csd_coef[2], cs = p.csd_coef[3], ds = p.csd_coef[4];
+    const float wb = p.csd_w[b];
+    float acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int64_t o = ((int64_t)b * 4 + c) * p.csd_hw + px;
+        const float et = e[0][c], eu = e[1][c], en = cur[c], nz = p.csd_noise[o];
+        float g = wb * (ct * et + cu * eu + cn * en + cs * nz);
+        if (isnan(g)) g = 0.f; else if (isinf(g)) g = g > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        if (p.csd_grad) p.csd_grad[o] = g;
+        if (p.csd_dlat) p.csd_dlat[o] = g * ds;
+        acc[0] += 0.5f * g * g; acc[1] += g * g;
+        acc[2] += (eu - nz) * (eu - nz); acc[3] += (et - nz) * (et - nz); acc[4] += (et - eu) * (et - eu);
+        acc[5] += (et - en) * (et - en); acc[6] += (en - eu) * (en - eu);
+        acc[7] += nz * nz; acc[8] += eu * eu; acc[9] += et * et;
+    }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const float sum = warp_sum(acc[q]);
+        if (lane == q) atomicAdd(p.csd_norms + q, sum);
+    }
+}
+
 // CPS = persistent CTAs per SM.  Two co-resident CTAs (each with its own single-thread MMA issuer and a ~96 KB operand
 // ring) keep the tensor pipe's queue fuller for the narrower tiles; 256-wide tiles need all of TMEM and run one per SM.
 template <int BN, int CPS> struct Cfg {
@@ -290,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
             const int slabs = p.is_conv ? (p.Cin / BK) : nk;
             const int tiles_w = p.is_conv ? p.Wo / p.tile_w : 1, tiles_h = p.is_conv ? p.Ho / p.tile_h : 1;
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int i = 0, t; (t = tile_at(p, i, blockIdx.x, gridDim.x, total_tiles)) >= 0; ++i) {
                 const int sp = t % S, tt = t / S;
                 const int z = tt / tiles_per_z, r = tt - z * tiles_per_z;
                 const int m_tile = r / n_tiles, n_tile = r - m_tile * n_tiles;
@@ -327,7 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
                                        ((uint32_t)(BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int i = 0, t; (t = tile_at(p, i, blockIdx.x, gridDim.x, total_tiles)) >= 0; ++i) {
                 const int sp = t % S;
                 const int kb0 = (int)((int64_t)sp * nk / S), kb1 = (int)((int64_t)(sp + 1) * nk / S);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
@@ -356,13 +425,22 @@ __global__ void __launch_bounds__(NTHREADS, CPS) tc_gemm_kernel(const __grid_con
         const int quarter = warp & 3;           // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;    // row inside the tile
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        float csd_e[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int i = 0, t; (t = tile_at(p, i, blockIdx.x, gridDim.x, total_tiles)) >= 0; ++i) {
             const int tt = t / S;
             const int z = tt / tiles_per_z, r_ = tt - z * tiles_per_z;
             const int m_tile = r_ / n_tiles, n_tile = r_ - m_tile * n_tiles;
             const int64_t m = (int64_t)m_tile * BM + row;
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            if constexpr (BN == 64 && !DUAL) {
+                if (p.csd) {
+                    epilogue_csd<BN, T>(p, tmem_base + (uint32_t)(acc * ACC_W) + ((uint32_t)(quarter * 32) << 16), m, lane,
+                                        tmem_empty_bar(acc), csd_e);
+                    if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+                    continue;
+                }
+            }
             epilogue_tile<BN, T, false, DUAL>(p, tmem_base + (uint32_t)(acc * ACC_W) + ((uint32_t)(quarter * 32) << 16), m, z, n_tile,
                                         lane, tmem_empty_bar(acc));
             if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -1031,6 +1109,7 @@ extern "C" int dm_gemm(int bf16, const void* A, int64_t lda, int64_t a_batch_str
                        int64_t b_batch_stride, void* C, int64_t ldc, int64_t c_batch_stride, int M, int N, int K,
                        int batch, const dm_epilogue* ep, int bn_hint, void* stream) {
     DM_REQUIRE(A && B && C, "null pointer");
+    DM_REQUIRE(bf16 == 0 || bf16 == 1, "16-bit operands only: fp32 storage goes through dm_hp_split -> bf16 GEMM -> dm_hp_epilogue");
     DM_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "K must be a positive multiple of 64");
     DM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "row strides must be multiples of 8 elements (16 bytes)");
     DM_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "16-byte aligned operands");
@@ -1075,6 +1154,7 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
                          int stride, int pad_t, int pad_l, int Ho, int Wo, void* y, int64_t ldc, const dm_epilogue* ep,
                          int bn_hint, void* stream) {
     DM_REQUIRE(x && w && y, "null pointer");
+    DM_REQUIRE(bf16 == 0 || bf16 == 1, "16-bit operands only: fp32 storage goes through dm_hp_split -> bf16 conv -> dm_hp_epilogue");
     DM_REQUIRE(Cin % BK == 0, "Cin must be a multiple of 64 (pad the channels)");
     DM_REQUIRE(ksize == 3 || ksize == 1, "3x3 or 1x1");
     DM_REQUIRE(stride == 1 || stride == 2, "stride 1 or 2");
@@ -1132,4 +1212,55 @@ extern "C" int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int C
     p.out = y; p.ldc = (int)ldc; p.out_batch_stride = 0;
     fill_epilogue(p, ep, Cout);
     return dispatch(tmA, tmB, p, tc, bf16, (cudaStream_t)stream);
+}
+
+
+// conv_out of the UNet with the CSD combination fused into its epilogue (SURVEY.md section 8b `dm_unet_fwd_sds`, north_star
+// "SDS noise-residual scale/weight fused into the final UNet epilogue").  x [3B, H, W, Cin] ordered [branch][view], 3x3, pad 1,
+// 4 output channels; replaces conv_out + `.sample` layout change + compute_grad_sds' tail (dreammat_guidance.py:274-282,475-495).
+extern "C" int dm_conv2d_csd(int bf16, const void* x, int B, int H, int W, int Cin, const void* w, const void* bias,
+                             const dm_csd* c, void* stream) {
+    DM_REQUIRE(x && w && c && c->noise && c->w && c->coef && c->norms, "null pointer");
+    DM_REQUIRE(bf16 == 0 || bf16 == 1, "16-bit storage only (fp32 mode uses conv_out + dm_sds_grad)");
+    DM_REQUIRE(Cin % BK == 0 && B > 0, "Cin must be a multiple of 64");
+    const int hw = H * W, n_img = 3 * B;
+    DM_REQUIRE(((int64_t)B * hw) % BM == 0, "views x latent pixels must be a multiple of 128");
+    int tile_w = W < BM ? W : BM;
+    int tile_h = (BM / tile_w) < H ? (BM / tile_w) : H;
+    int tile_n = BM / (tile_w * tile_h);
+    DM_REQUIRE(tile_w * tile_h * tile_n == BM && W % tile_w == 0 && H % tile_h == 0 && (tile_n == 1 || B % tile_n == 0),
+               "output extent must tile into 128-pixel boxes inside one branch");
+    const int Cout = 4, K = 9 * Cin;
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {BK, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_n}, es[4] = {1, 1, 1, 1};
+        int rc = encode_map(&tmA, bf16, x, 4, dims, str, box, es); if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)Cout, 1};
+        uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)K * Cout * 2};
+        uint32_t box[3] = {BK, 64, 1}, es[3] = {1, 1, 1};
+        int rc = encode_map(&tmB, bf16, w, 3, dims, str, box, es); if (rc) return rc;
+    }
+    GemmParams p; memset(&p, 0, sizeof(p));
+    p.M = n_img * hw; p.N = Cout; p.K = K; p.batch = 1; p.is_conv = 1; p.Cin = Cin; p.taps = 9; p.kw_n = 3;
+    p.Ho = H; p.Wo = W; p.tile_w = tile_w; p.tile_h = tile_h; p.tile_n = tile_n; p.stride = 1; p.pad_t = 1; p.pad_l = 1;
+    p.bias = bias; p.alpha = 1.0f; p.out_scale = 1.0f; p.rows_per_vec = 1; p.split_k = 1;
+    p.csd = 1; p.csd_B = B; p.csd_hw = hw; p.csd_groups = (int)(((int64_t)B * hw) / BM);
+    p.csd_noise = c->noise; p.csd_w = c->w; p.csd_coef = c->coef;
+    p.csd_grad = c->grad; p.csd_dlat = c->dlatents; p.csd_norms = c->norms; p.csd_eps = c->eps_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    // persistent single-CTA kernel, 64-wide tile, one CTA per tile GROUP (three row tiles)
+    auto launch_csd = [&](auto kern) -> int {
+        // (idempotent; the plain conv path sets the same attribute on the same instantiation)
+        DM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 2>::SMEM));
+        const int64_t slots = (int64_t)DM_NUM_SMS * 2;
+        const unsigned grid = (unsigned)(p.csd_groups < slots ? p.csd_groups : slots);
+        DM_CHECK_CUDA(dm_launch(kern, dim3(grid), dim3(NTHREADS), (size_t)Cfg<64, 2>::SMEM, st, tmA, tmB, p));
+        DM_CHECK_LAUNCH();
+        return DM_OK;
+    };
+    return bf16 ? launch_csd(tc_gemm_kernel<64, __nv_bfloat16, 2>) : launch_csd(tc_gemm_kernel<64, __half, 2>);
 }

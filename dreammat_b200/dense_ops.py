@@ -1,5 +1,9 @@
 """torch-facing wrappers of the dense-path C-ABI entry points (tensor-core GEMM / conv, norms,
-attention, elementwise).  Activations are NHWC fp16 (or bf16); accumulation is fp32."""
+attention, elementwise).  Activations are NHWC fp16 (or bf16); accumulation is fp32.
+
+fp32 tensors select the high-precision mode (half_precision_weights=false, dreammat_guidance.py:56,92-94): the
+contractions run on the same bf16 tensor-core kernel over 3-way split operands (csrc/dense_hp.cu), everything
+else on fp32 storage."""
 from __future__ import annotations
 
 import ctypes as C
@@ -36,11 +40,83 @@ def _ep(bias=None, rowvec=None, rows_per_vec=1, residual=None, ld_res=0, res_bat
 
 
 def _is_bf16(t):
+    """storage selector of the C-ABI: 0 fp16, 1 bf16, 2 fp32 (high-precision mode)."""
     if t.dtype == torch.bfloat16:
         return 1
     if t.dtype == torch.float16:
         return 0
-    raise TypeError(f"dense path expects fp16/bf16, got {t.dtype}")
+    if t.dtype == torch.float32:
+        return 2
+    raise TypeError(f"dense path expects fp16/bf16/fp32, got {t.dtype}")
+
+
+def _dt_code(dtype):
+    return {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[dtype]
+
+
+def hp_split(x2d, pattern):
+    """fp32 [rows, cols] (row stride allowed) -> bf16 [rows, 6*cols]; pattern 0: A operand, 1: B operand."""
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    rows, cols = x2d.shape
+    out = torch.empty(rows, 6 * cols, device=x2d.device, dtype=torch.bfloat16)
+    check(lib().dm_hp_split(ptr_any(x2d), rows, cols, x2d.stride(0), pattern, ptr_any(out), stream_ptr()), "dm_hp_split")
+    return out
+
+
+def _hp_rows(t):
+    """[.., R, C] view with a uniform row stride -> 2-D [rows, C] view (no copy when possible)."""
+    if t.dim() == 2:
+        return t
+    if t.stride(0) == t.shape[1] * t.stride(1):
+        return t.as_strided((t.shape[0] * t.shape[1], t.shape[2]), (t.stride(1), 1))
+    return t.contiguous().view(-1, t.shape[-1])
+
+
+def _hp_finish(raw, rows, N, rows_per_batch, e, out, ldc, out_bs):
+    check(lib().dm_hp_epilogue(ptr_any(raw), rows, N, rows_per_batch, C.byref(e), ptr_any(out), ldc, out_bs, stream_ptr()),
+          "dm_hp_epilogue")
+    return out
+
+
+def _hp_gemm(a, b, bias, rowvec, rows_per_vec, residual, alpha, out_scale, act, out, bn):
+    batched = a.dim() == 3
+    batch = a.shape[0] if batched else 1
+    M, K = a.shape[-2], a.shape[-1]
+    N = b.shape[-2]
+    a6 = hp_split(_hp_rows(a), 0)
+    b6 = hp_split(_hp_rows(b), 1)
+    raw = torch.empty(batch * M, N, device=a.device, dtype=torch.float32)
+    K6 = 6 * K
+    e0 = _ep(out_f32=True)
+    bshared = b.dim() == 2
+    check(lib().dm_gemm(1, ptr_any(a6), K6, M * K6, ptr_any(b6), K6, 0 if bshared else N * K6, ptr_any(raw), N, M * N, M, N, K6,
+                        batch, C.byref(e0), bn, stream_ptr()), "dm_gemm")
+    n_out = N // 2 if act == "geglu" else N
+    if out is None:
+        out = torch.empty((batch, M, n_out) if batched else (M, n_out), device=a.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.stride(-1) == 1
+    ld_res = residual.stride(-2) if residual is not None else 0
+    r_bs = residual.stride(0) if (residual is not None and residual.dim() == 3) else 0
+    e = _ep(bias, rowvec, rows_per_vec, residual, ld_res, r_bs, alpha, out_scale, act, True)
+    return _hp_finish(raw, batch * M, N, M, e, out, out.stride(-2), out.stride(0) if batched else 0)
+
+
+def _hp_conv2d(x, w, ksize, stride, pad, Ho, Wo, bias, rowvec, residual, out_scale, act, out, bn):
+    n, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    taps = ksize * ksize
+    x6 = hp_split(x.view(-1, Cin), 0).view(n, H, W, 6 * Cin)
+    w6 = hp_split(w.view(Cout * taps, Cin), 1).view(Cout, taps * 6 * Cin)
+    raw = torch.empty(n * Ho * Wo, Cout, device=x.device, dtype=torch.float32)
+    e0 = _ep(out_f32=True)
+    check(lib().dm_conv2d(1, ptr_any(x6), n, H, W, 6 * Cin, ptr_any(w6), Cout, ksize, stride, pad[0], pad[1], Ho, Wo,
+                          ptr_any(raw), Cout, C.byref(e0), bn, stream_ptr()), "dm_conv2d")
+    if out is None:
+        out = torch.empty(n, Ho, Wo, Cout, device=x.device, dtype=torch.float32)
+    assert out.dtype == torch.float32
+    ld_res = residual.stride(2) if residual is not None else 0
+    e = _ep(bias, rowvec, Ho * Wo, residual, ld_res, 0, 1.0, out_scale, act, True)
+    return _hp_finish(raw, n * Ho * Wo, Cout, n * Ho * Wo, e, out, out.stride(2), 0)
 
 
 _WORKSPACE = {}
@@ -64,6 +140,9 @@ def gemm(a, b, bias=None, rowvec=None, rows_per_vec=1, residual=None, alpha=1.0,
     _ensure_workspace()
     bf = _is_bf16(a)
     assert b.dtype == a.dtype
+    if bf == 2:
+        assert a.stride(-1) == 1 and b.stride(-1) == 1 and b.shape[-1] == a.shape[-1]
+        return _hp_gemm(a, b, bias, rowvec, rows_per_vec, residual, alpha, out_scale, act, out, bn)
     batched = a.dim() == 3
     batch = a.shape[0] if batched else 1
     M, K = a.shape[-2], a.shape[-1]
@@ -117,10 +196,40 @@ def conv2d(x, w, ksize, stride=1, pad=(1, 1), out_hw=None, bias=None, rowvec=Non
     if residual is not None:
         ld_res = residual.stride(2)
         assert residual.stride(-1) == 1 and residual.stride(1) == Wo * ld_res and residual.stride(0) == Ho * Wo * ld_res
+    if bf == 2:
+        return _hp_conv2d(x, w, ksize, stride, pad, Ho, Wo, bias, rowvec, residual, out_scale, act, out, bn)
     e = _ep(bias, rowvec, Ho * Wo, residual, ld_res, 0, 1.0, out_scale, act, out.dtype == torch.float32)
     check(lib().dm_conv2d(bf, ptr_any(x), n, H, W, Cin, ptr_any(w), Cout, ksize, stride, pad[0], pad[1], Ho, Wo,
                           ptr_any(out), ldc, C.byref(e), bn, stream_ptr()), "dm_conv2d")
     return out
+
+
+class Csd(C.Structure):
+    _fields_ = [("noise", C.c_void_p), ("w", C.c_void_p), ("coef", C.c_void_p), ("grad", C.c_void_p),
+                ("dlatents", C.c_void_p), ("norms", C.c_void_p), ("eps_out", C.c_void_p)]
+
+
+def csd_supported(x_dtype, B, h, w):
+    """the fused conv_out + CSD epilogue needs 16-bit storage and whole 128-row tiles inside one CFG branch"""
+    if x_dtype == torch.float32 or (B * h * w) % 128 != 0:
+        return False
+    tw = min(w, 128)
+    th = min(128 // tw, h)
+    tn = 128 // (tw * th)
+    return tw * th * tn == 128 and w % tw == 0 and h % th == 0 and (tn == 1 or B % tn == 0)
+
+
+def conv2d_csd(x, w, bias, noise, w1mac, coef, grad=None, dlat=None, norms=None, eps_out=None):
+    """conv_out + CSD combine in one kernel (dm_conv2d_csd).  x [3B,h,w,Cin] ordered [branch][view]; noise / grad / dlat
+    [B,4,h,w] fp32; coef = device tensor (c_text, c_uncond, c_null, c_noise, dlat_scale); norms[10] is accumulated into."""
+    bf = _is_bf16(x)
+    assert x.is_contiguous() and w.is_contiguous() and noise.is_contiguous() and coef.dtype == torch.float32
+    n3, h, ww, Cin = x.shape
+    B = n3 // 3
+    assert n3 == 3 * B and w.shape == (4, 9 * Cin) and noise.shape == (B, 4, h, ww) and norms is not None
+    c = Csd(noise.data_ptr(), w1mac.data_ptr(), coef.data_ptr(), grad.data_ptr() if grad is not None else None,
+            dlat.data_ptr() if dlat is not None else None, norms.data_ptr(), eps_out.data_ptr() if eps_out is not None else None)
+    check(lib().dm_conv2d_csd(bf, ptr_any(x), B, h, ww, Cin, ptr_any(w), ptr_any(bias), C.byref(c), stream_ptr()), "dm_conv2d_csd")
 
 
 def conv_weight_to_gemm(w_oihw: torch.Tensor, cin_pad: int = 0, cout_pad: int = 0, dtype=torch.float16):
@@ -259,7 +368,7 @@ def pad_convert(x_f32, cpad, scale=1.0, shift=0.0, dtype=torch.float16):
     cin = x_f32.shape[-1]
     rows = x_f32.numel() // cin
     y = torch.empty(*x_f32.shape[:-1], cpad, device=x_f32.device, dtype=dtype)
-    check(lib().dm_pad_convert(1 if dtype == torch.bfloat16 else 0, ptr_any(x_f32), rows, cin, cpad, scale, shift,
+    check(lib().dm_pad_convert(_dt_code(dtype), ptr_any(x_f32), rows, cin, cpad, scale, shift,
                                ptr_any(y), stream_ptr()), "dm_pad_convert")
     return y
 
@@ -304,7 +413,7 @@ def vae_sample_bwd(moments, eps, dz, scaling=0.18215):
 def add_noise(z, noise, sqrt_ac, sqrt_1mac, rep=3, cpad=64, dtype=torch.float16):
     B, _, Hh, W = z.shape
     out = torch.empty(rep * B, Hh, W, cpad, device=z.device, dtype=dtype)
-    check(lib().dm_add_noise(1 if dtype == torch.bfloat16 else 0, ptr_any(z.contiguous()), ptr_any(noise.contiguous()),
+    check(lib().dm_add_noise(_dt_code(dtype), ptr_any(z.contiguous()), ptr_any(noise.contiguous()),
                              ptr_any(sqrt_ac.contiguous()), ptr_any(sqrt_1mac.contiguous()), B, Hh * W, cpad, rep,
                              ptr_any(out), stream_ptr()), "dm_add_noise")
     return out
@@ -313,7 +422,7 @@ def add_noise(z, noise, sqrt_ac, sqrt_1mac, rep=3, cpad=64, dtype=torch.float16)
 def timestep_embedding(t_f32, dim=320, dtype=torch.float16):
     n = t_f32.shape[0]
     out = torch.empty(n, dim, device=t_f32.device, dtype=dtype)
-    check(lib().dm_timestep_embedding(1 if dtype == torch.bfloat16 else 0, ptr_any(t_f32.contiguous()), n, dim,
+    check(lib().dm_timestep_embedding(_dt_code(dtype), ptr_any(t_f32.contiguous()), n, dim,
                                       ptr_any(out), stream_ptr()), "dm_timestep_embedding")
     return out
 

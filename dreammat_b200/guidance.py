@@ -131,6 +131,12 @@ class _DenseGraphs:
         self.ctx = torch.zeros(3 * B, 77, Dm, device=dev, dtype=dt)
         self.cond = torch.zeros(B, H, W, 22, device=dev)
         self.dz = torch.zeros(B, 4, h, w, device=dev)
+        # fused conv_out + CSD epilogue (D.conv2d_csd): its schedule scalars live on the device so replays see new values
+        self.fused_csd = guid.fuse_csd and D.csd_supported(dt, B, h, w)
+        self.w1mac = torch.zeros(B, device=dev)
+        self.coef = torch.zeros(5, device=dev)
+        self.sums = torch.zeros(10, device=dev)
+        self.grad = torch.zeros(B, 4, h, w, device=dev)
         self.pool = torch.cuda.graph_pool_handle()
         self.cond_scale = None
         # eager warm-up on a side stream (first-launch attribute setup must not happen under capture)
@@ -168,7 +174,13 @@ class _DenseGraphs:
         if g.use_controlnet and scale != 0:
             cond = D.pad_convert(self.cond, 64, 1.0, 0.0, g.weights_dtype)
             down, mid = g.controlnet.forward(zt, self.t3, self.ctx, cond, scale)
-        self.eps = g.unet.forward(zt, self.t3, self.ctx, down, mid)
+        if self.fused_csd:
+            R.fill_(self.sums, 0.0)
+            g.unet.forward(zt, self.t3, self.ctx, down, mid,
+                           csd=dict(noise=self.noise, w1mac=self.w1mac, coef=self.coef, grad=self.grad, dlat=self.dz, norms=self.sums))
+            self.eps = None
+        else:
+            self.eps = g.unet.forward(zt, self.t3, self.ctx, down, mid)
 
     def _vae_bwd(self):
         g = self.guid
@@ -222,10 +234,15 @@ class StableDiffusionLightGuidance:
         grad_normalize: Optional[bool] = False
 
     def __init__(self, cfg: Optional[dict] = None, unet_cfg=None, vae_cfg=None, unet_weights=None, controlnet_weights=None,
-                 vae_weights=None, device="cuda", dtype=torch.float16):
+                 vae_weights=None, device="cuda", dtype=None):
         self.cfg = self.Config(**(cfg or {}))
         self.device = torch.device(device)
-        self.weights_dtype = dtype
+        # dreammat_guidance.py:92-94: fp16 weights unless half_precision_weights=false (then fp32 = the high-precision
+        # mode of the kernels, csrc/dense_hp.cu); an explicit dtype (bf16: BASELINE config 3) overrides
+        self.weights_dtype = dtype if dtype is not None else (torch.float16 if self.cfg.half_precision_weights else torch.float32)
+        self.fuse_csd = True          # conv_out + CSD combination in one kernel where the shape allows (D.csd_supported)
+        self.keep_debug = False       # parity tests: keep latents / eps / grad of the last evaluation in self.debug
+        self.debug: Dict[str, torch.Tensor] = {}
         self.use_controlnet = self.cfg.use_controlnet
         if self.use_controlnet and list(self.cfg.control_types) != ["light"]:
             # dreammat.yaml:62 selects ['light']; the annotator-based types need controlnet_aux (out of scope)
@@ -273,8 +290,9 @@ class StableDiffusionLightGuidance:
         return cond_bhwc
 
     @torch.no_grad()
-    def predict_noise(self, latents, t, noise, ctx3, cond_bhwc, condition_scale):
-        """compute_without_perpneg (:388-438): 3-branch batch [text | uncond | null] -> eps [3,B,4,h,w] fp32."""
+    def predict_noise(self, latents, t, noise, ctx3, cond_bhwc, condition_scale, csd=None):
+        """compute_without_perpneg (:388-438): 3-branch batch [text | uncond | null] -> eps [3,B,4,h,w] fp32
+        (or, with `csd`, straight into the fused CSD epilogue of conv_out: nothing returned)."""
         B = latents.shape[0]
         ac = self.alphas[t]
         zt = D.add_noise(latents, noise, ac.sqrt(), (1 - ac).sqrt(), rep=3, cpad=64, dtype=self.weights_dtype)
@@ -285,8 +303,8 @@ class StableDiffusionLightGuidance:
             cond = D.pad_convert(self._cond_to_latent_grid(cond_bhwc, latents.shape[-2], latents.shape[-1]), 64, 1.0, 0.0,
                                  self.weights_dtype)
             down, mid = self.controlnet.forward(zt, t3, ctx, cond, float(condition_scale))
-        eps = self.unet.forward(zt, t3, ctx, down, mid)
-        return eps.view(3, B, *eps.shape[1:])
+        eps = self.unet.forward(zt, t3, ctx, down, mid, csd=csd)
+        return eps.view(3, B, *eps.shape[1:]) if csd is None else None
 
     def compute_grad_sds(self, latents, cond_bhwc, ctx3, t=None, noise=None):
         """:440-497.  Returns (grad, dlatents, sums) with sums = the 10 squared diagnostic norms."""
@@ -296,10 +314,23 @@ class StableDiffusionLightGuidance:
         if noise is None:
             noise = torch.randn_like(latents)
         scale = self.cfg.condition_scales[0] if self.use_controlnet else 0.0
-        eps = self.predict_noise(latents.detach(), t, noise, ctx3, cond_bhwc, scale)
         w = (1 - self.alphas[t]).float()
-        return R.sds_grad(eps, noise, w, float(self.cond_scale), float(self.uncond_scale), float(self.null_scale),
-                          float(self.noise_scale))
+        if self.fuse_csd and D.csd_supported(self.weights_dtype, B, latents.shape[-2], latents.shape[-1]):
+            noise = noise.float().contiguous()
+            grad, dlat, sums = torch.empty_like(noise), torch.empty_like(noise), torch.zeros(10, device=self.device)
+            eps = torch.empty(3, *noise.shape, device=self.device) if self.keep_debug else None
+            coef = torch.tensor([float(self.cond_scale), float(self.uncond_scale), float(self.null_scale),
+                                 float(self.noise_scale), 1.0 / B], dtype=torch.float32).to(self.device)
+            self.predict_noise(latents.detach(), t, noise, ctx3, cond_bhwc, scale,
+                               csd=dict(noise=noise, w1mac=w.contiguous(), coef=coef, grad=grad, dlat=dlat, norms=sums, eps_out=eps))
+            out = (grad, dlat, sums)
+        else:
+            eps = self.predict_noise(latents.detach(), t, noise, ctx3, cond_bhwc, scale)
+            out = R.sds_grad(eps, noise, w, float(self.cond_scale), float(self.uncond_scale), float(self.null_scale),
+                             float(self.noise_scale))
+        if self.keep_debug:
+            self.debug = {"latents": latents.detach().clone(), "eps": eps.clone(), "grad": out[0].clone()}
+        return out
 
     # ---- CUDA-graph path: the dense section has static shapes, so its ~900 launches are captured once
     def enable_graphs(self, B: int, H: int, W: int):
@@ -333,13 +364,21 @@ class StableDiffusionLightGuidance:
         g.sqrt_ac.copy_(ac.sqrt()); g.sqrt_1mac.copy_((1 - ac).sqrt()); g.t3.copy_(torch.cat([t] * 3).float())
         g.ctx.copy_(ctx3)
         g.cond.copy_(self._cond_to_latent_grid(cond_bhwc, g.noise.shape[-2], g.noise.shape[-1]))
-        g.g_unet.replay()
+        if g.fused_csd:
+            # the CSD combination, nan_to_num, d loss / d latents and the logged norms come out of conv_out's epilogue
+            g.w1mac.copy_(1 - ac)
+            g.coef.copy_(torch.tensor([float(self.cond_scale), float(self.uncond_scale), float(self.null_scale),
+                                       float(self.noise_scale), grad_scale / B], dtype=torch.float32))
+            g.g_unet.replay()
+            sums = g.sums
+        else:
+            g.g_unet.replay()
+            grad, dlat, sums = R.sds_grad(g.eps.view(3, B, *g.eps.shape[1:]), g.noise, (1 - ac).float(), float(self.cond_scale),
+                                          float(self.uncond_scale), float(self.null_scale), float(self.noise_scale))
+            g.dz.copy_(dlat)
+            g.dz.mul_(grad_scale)
         if mark:
             mark("unet_cn")
-        grad, dlat, sums = R.sds_grad(g.eps.view(3, B, *g.eps.shape[1:]), g.noise, (1 - ac).float(), float(self.cond_scale),
-                                      float(self.uncond_scale), float(self.null_scale), float(self.noise_scale))
-        g.dz.copy_(dlat)
-        g.dz.mul_(grad_scale)
         g.g_bwd.replay()
         g.replayed_launches += g.n_vae + g.n_unet + g.n_bwd
         if mark:

@@ -205,9 +205,11 @@ class UNet(_UNetCommon):
         self._norm("conv_norm_out"); self._conv("conv_out")
         self._finish_tproj()
 
-    def forward(self, sample_nhwc, t_f32, ctx, down_res=None, mid_res=None):
+    def forward(self, sample_nhwc, t_f32, ctx, down_res=None, mid_res=None, csd=None):
         """sample [N,h,w,64] (4 real channels), ctx [N,77,D] -> eps [N,4,h,w] fp32 (values rounded to the
-        storage dtype, as the reference's `.sample.to(input_dtype)`)."""
+        storage dtype, as the reference's `.sample.to(input_dtype)`).
+        csd = dict(noise, w1mac, coef, grad, dlat, norms[, eps_out]): conv_out runs with the CSD combination fused
+        into its epilogue (D.conv2d_csd) and nothing is returned."""
         cfg, P = self.cfg, self.p
         tproj = self.time_embed(t_f32)
         sample = D.conv2d(sample_nhwc, P["conv_in.w"], 3, bias=P["conv_in.bias"])
@@ -235,6 +237,9 @@ class UNet(_UNetCommon):
                 sample = D.conv2d(D.upsample2x(sample), P[pn + ".w"], 3, bias=P[pn + ".bias"])
         h, _ = D.groupnorm(sample, P["conv_norm_out.weight"], P["conv_norm_out.bias"], cfg.norm_groups, 1e-5, silu=True)
         N_, H, W, _ = h.shape
+        if csd is not None:
+            D.conv2d_csd(h, P["conv_out.w"], P["conv_out.bias"], **csd)
+            return None
         out = torch.empty(N_, H, W, 8, device=self.dev, dtype=self.dt)
         D.conv2d(h, P["conv_out.w"], 3, bias=P["conv_out.bias"], out=out[..., :cfg.out_channels])
         return D.nhwc_to_nchw_f32(out, cfg.out_channels)

@@ -342,6 +342,13 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
                              float(grad_scale), stream_ptr()), "dm_adam_step")
 
 
+def fill_(t, value: float):
+    """t[:] = value through the library (capturable into a CUDA graph, counted in dm_launch_count)."""
+    assert t.is_contiguous() and t.dtype == torch.float32
+    check(lib().dm_fill(ptr(t), t.numel(), float(value), stream_ptr()), "dm_fill")
+    return t
+
+
 def sds_grad(eps_pred, noise, w, c_text, c_uncond, c_null, c_noise):
     """eps_pred [3,B,C,H,W] fp32 -> (grad [B,C,H,W], dlatents, sums[10])."""
     eps_pred, noise, w = _f32c(eps_pred), _f32c(noise), _f32c(w)

@@ -326,12 +326,26 @@ class DreamMat:
         self.global_step = 0
         self.world_size, self.rank = 1, 0
         self.balance_pixels = True     # multi-GPU: shade equal pixel intervals of the global batch (parallel.pixel_partition)
+        self._balance_ok = False       # set by prepare_balanced(): EVERY rank holds every fixed view's G-buffer
         # dreammat_guidance.py:507-513: renders that are not 512x512 are resized (bilinear) to 512x512 before the VAE
         self.resize_to_vae = True
 
     def C(self, v):
         from .guidance import C
         return C(v, 0, self.global_step)
+
+    def prepare_balanced(self, view_ids) -> bool:
+        """Decide ONCE, identically on every rank, whether pixel-balanced shading may be used: it needs every view of
+        `view_ids` in every rank's G-buffer cache.  The local answer is MIN-reduced over the ranks, so no rank can take
+        the all-to-all branch while another goes straight to the gradient all-reduce (mismatched collectives)."""
+        ok = all(int(v) in self.renderer._cache for v in view_ids)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(int(flag.item()))
+        self._balance_ok = ok
+        return ok
 
     def forward(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         return self.renderer(**batch)
@@ -396,10 +410,13 @@ class DreamMat:
         # `global_env_id`, every view in the G-buffer cache) the covered pixels of ALL views are cut into equal intervals
         # (parallel.pixel_partition) so the ray-tracing load does not depend on which views a rank drew.
         balanced = (self.world_size > 1 and self.balance_pixels and rng is None and "global_view_id" in batch and
-                    all(int(v) in ren._cache for v in batch["global_view_id"]))
+                    self._balance_ok)      # rank-invariant: fixed by prepare_balanced(), never by local cache state
         if balanced:
             from .parallel import exchange_rows, pixel_partition
             gvid = [int(v) for v in batch["global_view_id"]]
+            missing = [v for v in gvid if v not in ren._cache]
+            if missing:
+                raise RuntimeError(f"balanced shading was agreed on by all ranks but views {missing[:4]} are not cached here")
             geid = [int(e) for e in batch["global_env_id"]]
             pn_global = [ren._cache[v]["pn"] for v in gvid]
             if total_pn_global is None:
@@ -415,6 +432,11 @@ class DreamMat:
         g_ = getattr(guid, "graphs", None)
         resize = self.resize_to_vae and (H != 512 or W != 512)
         use_graphs = g_ is not None and g_.B == B and rng is None
+        if use_graphs:
+            want_hw = (512, 512) if resize else (H, W)      # the graphs are captured at the VAE input size
+            if tuple(g_.rgb.shape[1:3]) != want_hw:
+                raise RuntimeError(f"dense graphs were captured at {tuple(g_.rgb.shape[1:3])}, this step feeds the VAE {want_hw}: "
+                                   "call guidance.enable_graphs(B, 512, 512) for renders that are resized")
         canvas = g_.rgb.view(B, H * W, 3) if (use_graphs and not resize) else torch.empty(B, H * W, 3, device=dev)
         raw = torch.empty(B, H * W, 3, device=dev)            # canvas before the antialias blend
         check(lib().dm_fill(ptr(raw), raw.numel(), 1.0, st), "dm_fill")

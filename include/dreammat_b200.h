@@ -220,7 +220,42 @@ int dm_conv2d(int bf16, const void* x, int n_img, int H, int W, int Cin, const v
               int stride, int pad_t, int pad_l, int Ho, int Wo, void* y, int64_t ldc, const dm_epilogue* ep,
               int bn_hint, void* stream);
 
-/* ---- streaming kernels of the dense path (NHWC, fp16/bf16 storage selected by `bf16`, fp32 math) ---- */
+/* conv_out of the UNet with the CSD / SDS combination fused into its epilogue: the model-level tail of
+ * `dm_unet_fwd_sds`.  Replaces conv_out (dreammat_guidance.py:274-282), the `.sample` layout /
+ * dtype change and compute_grad_sds' tail + nan_to_num + the logged norms (:475-495, :584-594) by one kernel: a CTA
+ * computes the three CFG-branch tiles of the same 128 latent pixels back to back and combines them in registers.
+ * x [3B, H, W, Cin] NHWC ordered [branch: text | uncond | null][view]; w [4, 9*Cin]; bias [4] (storage dtype).
+ * noise [B,4,H*W] fp32, w1mac[B] = 1 - alphas_cumprod[t]; coef (DEVICE, so a captured graph can be replayed with new
+ * schedule values) = {c_text, c_uncond, c_null, c_noise, dlat_scale}.  Outputs (NCHW fp32): grad, dlatents = grad *
+ * dlat_scale (either may be NULL), norms[10] += the squared sums listed at dm_sds_grad, eps_out [3,B,4,H*W] optional. */
+typedef struct {
+    const float* noise;
+    const float* w;
+    const float* coef;
+    float* grad;
+    float* dlatents;
+    float* norms;
+    float* eps_out;
+} dm_csd;
+int dm_conv2d_csd(int bf16, const void* x, int B, int H, int W, int Cin, const void* w, const void* bias, const dm_csd* c,
+                  void* stream);
+
+/* ---- high-precision mode (half_precision_weights=false, models/guidance/dreammat_guidance.py:56,92-94) ----
+ * fp32 storage end to end.  The contractions still run on the bf16 tcgen05 kernel: both operands are split into three
+ * bf16 terms (24 mantissa bits) and the six significant partial products are laid side by side along K,
+ *     A' = [a1|a2|a1|a3|a2|a1],  B' = [b1|b1|b2|b1|b2|b3]   (K' = 6K; for a conv: 6*Cin channels per tap),
+ * so dm_gemm / dm_conv2d(bf16=1, out_f32=1, no epilogue terms) return A.B^T to fp32 accuracy; dm_hp_epilogue then
+ * applies the dm_epilogue terms (all pointers fp32) to the raw accumulators.  Every streaming entry point below
+ * accepts 2 as its `bf16` selector = fp32 storage.
+ * dm_hp_split: x [rows, ldx] (first `cols` columns) fp32 -> out [rows, 6*cols] bf16; pattern 0 = A operand, 1 = B operand
+ * (conv weights [Cout, taps*Cin]: rows = Cout*taps, cols = Cin). */
+int dm_hp_split(const float* x, int64_t rows, int cols, int64_t ldx, int pattern, void* out_bf16, void* stream);
+/* raw [rows, N] fp32 accumulators -> out (row stride ldc, batch stride out_batch_stride, rows_per_batch rows per batch):
+ * acc*alpha + bias + rowvec -> act -> + residual -> * out_scale; act 3 (GEGLU) writes N/2 columns */
+int dm_hp_epilogue(const float* raw, int64_t rows, int N, int64_t rows_per_batch, const dm_epilogue* ep, float* out,
+                   int64_t ldc, int64_t out_batch_stride, void* stream);
+
+/* ---- streaming kernels of the dense path (NHWC; storage selected by `bf16`: 0 fp16, 1 bf16, 2 fp32; fp32 math) ---- */
 /* torch.nn.GroupNorm (+ optional SiLU) as used by diffusers ResnetBlock2D / Transformer2DModel.norm.
  * x [n_img, HW, ld] (first C channels), y [n_img, HW, ldy]; stats [n_img*G*2] receives (sum, sumsq)
  * per group and is what dm_groupnorm_bwd needs. */

@@ -259,9 +259,9 @@ def sds_grad(eps_text, eps_uncond, eps_null, noise, t, ac, c, u, n, s):
 
 
 def guidance_step(wv, wc, wu, ucfg: UNetConfig, vcfg: VAEConfig, rgb_bhwc, cond_bhwc, ctx3, t, noise, vae_eps,
-                  scales=(1.05, -1.0, 0.0, 0.0), cond_scale=1.0, q: Callable = Ident):
+                  scales=(1.05, -1.0, 0.0, 0.0), cond_scale=1.0, q: Callable = Ident, return_eps: bool = False):
     """StableDiffusionLightGuidance.__call__ (:536-602) for explicit randomness (appendix B #7-#9).
-    ctx3 [3B,77,D] ordered [text | uncond | null].  Returns (loss_sds, grad, latents)."""
+    ctx3 [3B,77,D] ordered [text | uncond | null].  Returns (loss_sds, grad, latents[, eps [3,B,4,h,w]])."""
     B = rgb_bhwc.shape[0]
     x = rgb_bhwc.permute(0, 3, 1, 2)
     if x.shape[-1] != 512 or x.shape[-2] != 512:
@@ -279,6 +279,8 @@ def guidance_step(wv, wc, wu, ucfg: UNetConfig, vcfg: VAEConfig, rgb_bhwc, cond_
         grad = sds_grad(et, eu, en, noise, t, ac, *scales)
     target = (z - grad).detach()
     loss = 0.5 * F.mse_loss(z, target, reduction="sum") / B
+    if return_eps:
+        return loss, grad, z, e.view(3, B, *e.shape[1:])
     return loss, grad, z
 
 

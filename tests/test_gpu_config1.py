@@ -1,0 +1,137 @@
+"""BASELINE.json configs[0]: 1 view, 128x128 render, pre-baked condition maps, 5 SDS steps, fp32 weights
+(`half_precision_weights=false`, dreammat_guidance.py:56,92-94) -- the product (high-precision mode, csrc/dense_hp.cu)
+against the pure fp32 CPU oracle on identical inputs and randomness, FULL-SIZE SD-2.1-base topology (random init: no
+checkpoint exists on the box).  As in the reference, the 128^2 render and the condition maps are resized (bilinear) to
+512^2 before the VAE / ControlNet (dreammat_guidance.py:507-534), so the dense half runs at its real size.
+
+north_star tolerance: 1e-3 relative on rendered RGB and on the SDS gradient; asserted here on rgb, latents, the three eps
+branches, the SDS gradient and the flat parameter gradient of EVERY step, and on the Adam-updated parameters after 5 steps.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import render as OR
+from oracle import sd as OS
+from tests._fixtures import make_scene, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+TOL = 1e-3
+
+
+def _resize512(x_bhwc):
+    return F.interpolate(x_bhwc.permute(0, 3, 1, 2), (512, 512), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+
+
+def test_config1_fp32_five_steps_match_oracle():
+    from dreammat_b200 import antialias as AA
+    from dreammat_b200 import weights as Wt
+    from dreammat_b200.guidance import PromptProcessorOutput, StableDiffusionLightGuidance
+    from dreammat_b200.system import DreamMat, DreamMatMaterial, DreamMatMesh, RaytraceRender
+    dev, res, steps = "cuda", 128, 5
+    sc = make_scene(res=res, subdiv=3, bump=0.12, seed=3, n_views=2)     # the step alternates between two fixed views
+    ucfg, vcfg = OS.UNetConfig(), OS.VAEConfig()
+    wu, wc, wv = OS.random_unet_weights(ucfg, 0), OS.random_controlnet_weights(ucfg, 1), OS.random_vae_weights(vcfg, 2)
+    g = torch.Generator().manual_seed(21)
+    envs = [OR.synthetic_envmap(64, 128, seed=i) for i in range(5)]
+    geo = DreamMatMesh({"shape_init": "x"}, dev, mesh=(sc["v"], sc["f"]), seed=5)
+    geo.params[:geo.n_grid] = ((torch.rand(geo.n_grid, generator=g) * 2 - 1) * 0.5).to(dev)
+    p0 = geo.params.detach().cpu().clone()
+    mat = DreamMatMaterial({"diffuse_sample_num": 200, "specular_sample_num": 128, "use_bump": False}, dev, envs)
+    ren = RaytraceRender({}, geo, mat, None, dev)
+    # configs/dreammat.yaml:54-70 guidance block with fp32 weights
+    gcfg = dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05,
+                uncond_scale=[0, -1.0, -0.5, 2000], null_scale=[0, 0.0, -0.5, 2000], noise_scale=0.0, half_precision_weights=False)
+    guid = StableDiffusionLightGuidance(gcfg, Wt.UNetConfig(**ucfg.__dict__), Wt.VAEConfig(**vcfg.__dict__), wu, wc, wv, dev)
+    assert guid.weights_dtype == torch.float32
+    guid.keep_debug = True
+    vd, uvd, null = torch.randn(4, 77, 1024, generator=g), torch.randn(4, 77, 1024, generator=g), torch.randn(1, 77, 1024, generator=g)
+    pu = PromptProcessorOutput(vd[:1], uvd[:1], null, vd, uvd)
+    sysm = DreamMat(None, geo, mat, ren, guid, pu, dev)
+    assert sysm.resize_to_vae                                  # 128^2 -> 512^2 before the VAE, as the reference does
+    gb = sc["gb"]
+    views = []
+    for b in range(2):
+        sel = gb["selector"][b]
+        pix = torch.nonzero(sel).view(-1).int()
+        v = dict(pix=pix, pts=gb["gb_pos"][b][sel], nrm=gb["gb_normal"][b][sel], vd=gb["gb_viewdirs"][b][sel], n=int(pix.shape[0]))
+        d_, s_, a_ = AA.build_pairs(gb["rast"][b].numpy(), sc["v"].numpy(), sc["f"].numpy().astype(np.int64), ren._nbr_opp,
+                                    sc["cam"]["mvp_mtx"][b].numpy())
+        v["aa_oracle"] = OR.antialias_pairs(gb["rast"][b], sc["v"], sc["f"], sc["cam"]["mvp_mtx"][b])
+        ren._cache[100 + b] = {"pix": pix.to(dev), "pn": v["n"], "pts": v["pts"].to(dev).contiguous(), "nrm": v["nrm"].to(dev).contiguous(),
+                               "vd": v["vd"].to(dev).contiguous(),
+                               "aa": (torch.from_numpy(d_).to(dev), torch.from_numpy(s_).to(dev), torch.from_numpy(a_).to(dev))}
+        views.append(v)
+    el_all, az_all, dist_all = torch.tensor([15.0, -10.0]), torch.tensor([30.0, 160.0]), torch.tensor([3.2, 3.6])
+    # pre-baked condition maps (depth 1 + normal 3 + 6 light RGB = 22 channels), 8-bit like the PNGs of data/uncond.py:532-557
+    cond_all = torch.round(torch.rand(2, res, res, 22, generator=g) * 255) / 255
+
+    class _N:
+        def __getitem__(self, i):
+            return None
+
+    # ---------------- oracle state
+    meta, _ = OR.hashgrid_meta()
+    P = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([P], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    always_big = torch.ones_like(p0, dtype=torch.bool)
+    worst = {}
+    for step in range(steps):
+        b = step % 2
+        v = views[b]
+        n = v["n"]
+        rng = dict(rand_ang=[torch.rand(n, 1, generator=g)], normal_eps=[torch.randn(n, 1, generator=g) * 0.05],
+                   rand_d=[torch.rand(n, 1, 1, generator=g)], rand_s=[torch.rand(n, 1, 1, generator=g)],
+                   t=torch.randint(20, 981, (1,), generator=g), noise=torch.randn(1, 4, 64, 64, generator=g),
+                   vae_eps=torch.randn(1, 4, 64, 64, generator=g))
+        env_id = torch.tensor([(2 * step + 1) % 5])
+        el, az, dist = el_all[b:b + 1], az_all[b:b + 1], dist_all[b:b + 1]
+        cond = cond_all[b:b + 1]
+        batch = {"view_id": torch.tensor([100 + b]), "env_id": env_id, "height": res, "width": res, "rays_o": _N(), "rays_d": _N(),
+                 "mvp_mtx": sc["cam"]["mvp_mtx"][b:b + 1].to(dev), "w2c": sc["cam"]["w2c"][b:b + 1].to(dev), "elevation": el,
+                 "azimuth": az, "camera_distances": dist, "condition_map": cond.to(dev)}
+        assert sysm.global_step == step
+        out = sysm.training_step_fused(batch, rng=rng)
+        g_dev = geo.grads.detach().cpu().clone()
+        dbg = {k: x.cpu() for k, x in guid.debug.items()}
+
+        # ---------------- oracle step
+        grid, W1, W2 = P[:geo.n_grid], P[geo.n_grid:geo.n_grid + geo.n_w1].view(64, 32), P[geo.n_grid + geo.n_w1:].view(5, 64)
+        f = OR.geometry_forward(v["pts"], grid, W1, W2, meta)
+        fj = OR.geometry_forward(OR.jitter_positions(v["pts"], v["nrm"], rng["rand_ang"][0], rng["normal_eps"][0]), grid, W1, W2, meta)
+        al, me, ro, _ = OR.material_params(f, fj)
+        o = OR.shade_raytracing(v["pts"], v["nrm"], v["vd"], envs[int(env_id[0])], me, ro, al, rng["rand_d"][0], rng["rand_s"][0],
+                                lambda oo, dd: sc["tracer"].trace(oo, dd)[1])
+        c = torch.ones(res * res, 3).index_put((v["pix"].long(),), o["color"])
+        comp = OR.antialias_apply(c, v["aa_oracle"]).view(1, res, res, 3)
+        reg = OR.material_smoothness_grad(torch.sigmoid(f), torch.sigmoid(fj))
+        ctx3 = pu.get_text_embeddings(el, az, dist, True, return_null_text_embeddings=True)
+        scales = (1.05, OS.C(gcfg["uncond_scale"], 0, step), OS.C(gcfg["null_scale"], 0, step), 0.0)
+        loss_sds, grad_o, z_o, eps_o = OS.guidance_step(wv, wc, wu, ucfg, vcfg, _resize512(comp), _resize512(cond), ctx3, rng["t"],
+                                                        rng["noise"], rng["vae_eps"], scales=scales, cond_scale=1.0, return_eps=True)
+        opt.zero_grad()
+        (loss_sds + reg).backward()
+        e = {"rgb": rel_err(out["comp_rgb"].cpu(), comp.detach()), "latents": rel_err(dbg["latents"], z_o.detach()),
+             "eps_text": rel_err(dbg["eps"][0], eps_o[0]), "eps_uncond": rel_err(dbg["eps"][1], eps_o[1]),
+             "eps_null": rel_err(dbg["eps"][2], eps_o[2]), "sds_grad": rel_err(dbg["grad"], grad_o),
+             "loss_sds": abs(float(out["loss_sds"]) - float(loss_sds)) / abs(float(loss_sds)),
+             "mat_reg": abs(float(out["loss_mat_reg"]) - float(reg)) / abs(float(reg)), "param_grad": rel_err(g_dev, P.grad)}
+        print(f"\nconfig1 step {step}: " + " ".join(f"{k}={x:.2e}" for k, x in e.items()))
+        for k, x in e.items():
+            worst[k] = max(worst.get(k, 0.0), x)
+        ga = P.grad.abs()
+        always_big &= (ga > 1e-3 * ga.max()) | (ga == 0)
+        opt.step()
+    p5 = geo.params.detach().cpu()
+    d_dev, d_ref = p5 - p0, P.detach() - p0
+    moved = d_ref != 0
+    e_all = rel_err(d_dev[moved], d_ref[moved])
+    sel = moved & always_big
+    e_sel = rel_err(d_dev[sel], d_ref[sel])
+    print(f"\nconfig1 after {steps} Adam steps: update rel err {e_all:.2e} over all {int(moved.sum())} touched parameters, "
+          f"{e_sel:.2e} over the {int(sel.sum())} whose gradient never fell below 1e-3 of the largest (Adam's eps=1e-15 step is "
+          f"sign-like: a parameter whose gradient is at rounding level moves by +-lr whatever its value)")
+    print("config1 worst over steps: " + " ".join(f"{k}={x:.2e}" for k, x in worst.items()))
+    assert max(worst.values()) < TOL, worst
+    assert e_sel < TOL

@@ -235,6 +235,90 @@ def test_guidance_step_matches_oracle(small):
     assert e_g < max(2 * floor, TOL16) and e_r < max(3 * floor, 3 * TOL16)
 
 
+def test_fused_csd_epilogue_matches_unfused(small):
+    """J1: conv_out with the CSD combination fused into its epilogue (dm_conv2d_csd) against conv_out + layout change +
+    dm_sds_grad on the same UNet activations: the noise predictions must be identical and grad / dlatents / the ten
+    logged sums equal to fp32 reduction order."""
+    from dreammat_b200.guidance import PromptProcessorOutput, StableDiffusionLightGuidance
+    ucfg, vcfg, wu, wc, wv = small
+    g = torch.Generator().manual_seed(9)
+    Dm = ucfg.cross_attention_dim
+    for (B, hw) in ((2, 16), (4, 8), (1, 32)):
+        lat = torch.randn(B, 4, hw, hw, generator=g).cuda()
+        noise = torch.randn(B, 4, hw, hw, generator=g).cuda()
+        cond = torch.rand(B, 8 * hw, 8 * hw, 22, generator=g).cuda()
+        ctx3 = torch.randn(3 * B, 77, Dm, generator=g)
+        t = torch.randint(20, 981, (B,), generator=g).cuda()
+        cfg = dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05, uncond_scale=-0.7,
+                   null_scale=-0.2, noise_scale=0.1)
+        guid = StableDiffusionLightGuidance(cfg, ucfg, vcfg, wu, wc, wv)
+        guid.keep_debug = True
+        from dreammat_b200 import dense_ops as D
+        assert D.csd_supported(torch.float16, B, hw, hw)
+        guid.fuse_csd = True
+        g1, d1, s1 = guid.compute_grad_sds(lat, cond, ctx3, t, noise)
+        e1 = guid.debug["eps"].clone()
+        guid.fuse_csd = False
+        g0, d0, s0 = guid.compute_grad_sds(lat, cond, ctx3, t, noise)
+        e0 = guid.debug["eps"]
+        errs = dict(eps=rel(e1, e0), grad=rel(g1, g0), dlat=rel(d1, d0), sums=float(((s1 - s0).abs() / s0.abs().clamp_min(1e-20)).max()))
+        print(f"\nfused CSD epilogue B={B} {hw}x{hw}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+        assert errs["eps"] == 0.0 and errs["grad"] < 1e-6 and errs["dlat"] < 1e-6 and errs["sums"] < 1e-5, errs
+
+
+@pytest.mark.slow
+def test_vae_and_controlnet_full_size_match_oracle():
+    """Full-size SD-2.1-base VAE encoder (128,256,512,512) forward + input gradient at 512^2 and full-size ControlNet
+    (22-channel condition at 512^2, 64^2 latents) in the default fp16 mode vs the fp16-emulating oracle.  The bound is the
+    measured fp16 floor (oracle fp16-emulation vs oracle fp32, printed), x2."""
+    from dreammat_b200 import dense_ops as D
+    from dreammat_b200.nets import ControlNet, VAEEncoder
+    vcfg, ucfg = O.VAEConfig(), O.UNetConfig()
+    wv = O.round_weights(O.random_vae_weights(vcfg, 2))
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.rand(1, 512, 512, 3, generator=g)
+    eps = torch.randn(1, 4, 64, 64, generator=g)
+    dz = torch.randn(1, 4, 64, 64, generator=g)
+    ref = {}
+    for name, q in (("16", Q), ("32", O.Ident)):
+        x = (rgb * 2 - 1).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        mom_r = O.vae_encode_moments(wv, vcfg, q(x), q=q)
+        z_r = O.vae_sample(mom_r, eps, vcfg.scaling_factor, q)
+        z_r.backward(dz)
+        ref[name] = (mom_r.detach(), z_r.detach(), x.grad.clone())
+    vae = VAEEncoder(wv, vcfg)
+    tape = []
+    mom = vae.encode_moments(D.pad_convert(rgb.cuda(), 64, 2.0, -1.0), tape)
+    z = D.vae_sample(mom, eps.cuda(), vcfg.scaling_factor)
+    dx = vae.backward_input(tape, D.vae_sample_bwd(mom, eps.cuda(), dz.cuda(), vcfg.scaling_factor))
+    got = (nchw(mom, 8), z, nchw(dx, 3))
+    names = ("moments", "latents", "input-grad")
+    e = [rel(a, b) for a, b in zip(got, ref["16"])]
+    floor = [rel(a, b) for a, b in zip(ref["16"], ref["32"])]
+    print("\nvae full-size 512^2: " + " ".join(f"{n} {x:.2e} (fp16 floor {f:.2e})" for n, x, f in zip(names, e, floor)))
+    for x, f in zip(e, floor):
+        assert x < max(2 * f, 2e-3)
+    del vae, tape, mom, dx
+    torch.cuda.empty_cache()
+    wc = O.round_weights(O.random_controlnet_weights(ucfg, 1))
+    zz = torch.randn(3, 4, 64, 64, generator=g)
+    t = torch.tensor([400, 400, 400])
+    ctx = torch.randn(3, 77, 1024, generator=g)
+    cond = torch.rand(1, 22, 512, 512, generator=g)
+    with torch.no_grad():
+        d16, m16 = O.controlnet_forward(wc, ucfg, Q(zz), t, Q(ctx), Q(cond), 0.8, q=Q)
+        d32, m32 = O.controlnet_forward(wc, ucfg, Q(zz), t, Q(ctx), Q(cond), 0.8)
+    net = ControlNet(wc, ucfg)
+    down, mid = net.forward(D.pad_convert(zz.permute(0, 2, 3, 1).contiguous().cuda(), 64), t.float().cuda(), ctx.half().cuda(),
+                            D.pad_convert(cond.permute(0, 2, 3, 1).contiguous().cuda(), 64), 0.8)
+    errs = [rel(nchw(a), b) for a, b in zip(down, d16)] + [rel(nchw(mid), m16)]
+    floors = [rel(a, b) for a, b in zip(d16, d32)] + [rel(m16, m32)]
+    print("controlnet full-size: max rel err %.2e (fp16 floor max %.2e)" % (max(errs), max(floors)))
+    assert len(down) == 12
+    for x, f in zip(errs, floors):
+        assert x < max(2 * f, 2e-3)
+
+
 @pytest.mark.slow
 def test_unet_full_size_matches_oracle():
     """SD-2.1-base topology (865.9 M parameters, random init), one view = 3 CFG samples at 64x64 latents."""
