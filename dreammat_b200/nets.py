@@ -311,7 +311,8 @@ class VAEEncoder(_Base):
     differentiates through it every step."""
 
     def __init__(self, w, cfg, device="cuda", dtype=torch.float16):
-        super().__init__(w, device, dtype)
+        from .weights import normalize_vae_keys
+        super().__init__(normalize_vae_keys(w), device, dtype)     # legacy query/key/value/proj_attn names -> to_q/...
         self.cfg = cfg
         ch = cfg.block_out_channels
         self._conv("encoder.conv_in", cin_pad=64); self._conv_dgrad("encoder.conv_in", cin_pad=64)

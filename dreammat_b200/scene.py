@@ -278,6 +278,14 @@ def load_reference_envmaps(environment_texture: str, n: int = 5):
     return [load_hdr_image(os.path.join(environment_texture, f"map{i}", f"map{i}.exr")) for i in range(1, n + 1)]
 
 
+def load_fg_lut(path: str = "load/lights/bsdf_256_256.bin") -> torch.Tensor:
+    """The split-sum BRDF table `FG_LUT` (dreammat_material.py:405-410): 256 x 256 x 2 float32, [1, 256, 256, 2]."""
+    a = np.fromfile(path, dtype=np.float32)
+    if a.size != 256 * 256 * 2:
+        raise ValueError(f"{path}: expected 131072 float32 values, found {a.size}")
+    return torch.from_numpy(a.reshape(1, 256, 256, 2))
+
+
 def synthetic_envmap(H=512, W=1024, seed=0) -> torch.Tensor:
     """HDR lat-long map standing in for load/lights/envmap/map{1..5}.exr (100 MB each; absent on the GPU box)."""
     g = torch.Generator().manual_seed(seed)

@@ -79,6 +79,9 @@ class DreamMatMesh:
             v, f = mesh
         elif self.cfg.shape_init.startswith("mesh:"):
             assert isinstance(self.cfg.shape_init_params, float)
+            import os
+            if not os.path.exists(self.cfg.shape_init[5:]):
+                raise ValueError(f"Mesh file {self.cfg.shape_init[5:]} does not exist.")
             vv, ff = load_obj(self.cfg.shape_init[5:])
             v = torch.from_numpy(normalize_mesh(vv, self.cfg.shape_init_params, self.cfg.shape_init_mesh_up,
                                                 self.cfg.shape_init_mesh_front).astype(np.float32))
@@ -87,6 +90,9 @@ class DreamMatMesh:
             raise ValueError(f"Unknown shape initialization type: {self.cfg.shape_init}")
         self.v_pos, self.t_pos_idx = v.float().contiguous(), f.int().contiguous()
         self.v_nrm = vertex_normals(self.v_pos, self.t_pos_idx)
+        # the reference unwraps UVs with xatlas for its (hot-path-unused) vtex_buffer; kept as zeros for checkpoint shape parity
+        self.v_tex = torch.zeros(self.v_pos.shape[0], 2)
+        self._bound = None      # (grid, W1, W2) nn.Parameters of the plugin layer, sharing this object's flat storage
 
     def _views(self, flat):
         g = flat[:self.n_grid]
@@ -97,11 +103,33 @@ class DreamMatMesh:
     def isosurface(self):
         return self
 
+    def bind_parameters(self, grid_p, W1_p, W2_p):
+        """The plugin layer's nn.Parameters (views of self.params): the autograd path differentiates w.r.t. THEM, so
+        `loss.backward()` leaves the gradients where the optimizer looks (threestudio_plugin.DreamMatMesh)."""
+        assert grid_p.data_ptr() == self.grid.data_ptr() and W1_p.data_ptr() == self.W1.data_ptr() and W2_p.data_ptr() == self.W2.data_ptr()
+        self._bound = (grid_p, W1_p, W2_p)
+
+    def autograd_leaves(self):
+        """(grid, W1, W2) to differentiate with respect to on the autograd path: the bound nn.Parameters, else leaf
+        tensors aliasing the flat buffer created once (their .grad is what `grads_from_autograd` collects)."""
+        if self._bound is None:
+            self._bound = tuple(t.detach().requires_grad_(True) for t in (self.grid, self.W1, self.W2))
+        return self._bound
+
+    def grads_from_autograd(self):
+        """Copy the .grad of the autograd leaves into the flat gradient buffer (what optimizer_step consumes)."""
+        for leaf, dst in zip(self.autograd_leaves(), (self.dgrid, self.dW1, self.dW2)):
+            if leaf.grad is None:
+                dst.zero_()
+            else:
+                dst.copy_(leaf.grad)
+                leaf.grad = None
+
     def forward(self, points: torch.Tensor, output_normal: bool = False) -> Dict[str, torch.Tensor]:
         """dreammat_mesh.py:239-254 (autograd path; the fused step calls the kernels directly)."""
         assert output_normal is False, "Normal output is not supported for DreamMatMesh"
-        g = self.grid.detach().requires_grad_(True)
-        return {"features": R.hashgrid_mlp(points.view(-1, 3), g, self.W1, self.W2, self.hg).view(*points.shape[:-1], -1)}
+        g, w1, w2 = self.autograd_leaves()
+        return {"features": R.hashgrid_mlp(points.view(-1, 3), g, w1, w2, self.hg).view(*points.shape[:-1], -1)}
 
     __call__ = forward
 
@@ -287,9 +315,9 @@ class RaytraceRender:
             eps = torch.randn(n, 1, device=self.device) * self.change_eps            # appendix B #4
             pj = R.jitter_positions(g["pts"], g["nrm"], ang, eps)
             geo = self.geometry
-            grid = geo.grid if geo.grid.requires_grad else geo.grid.detach().requires_grad_(True)
-            f = R.hashgrid_mlp(g["pts"], grid, geo.W1, geo.W2, geo.hg)
-            fj = R.hashgrid_mlp(pj, grid, geo.W1, geo.W2, geo.hg)
+            grid, w1, w2 = geo.autograd_leaves()
+            f = R.hashgrid_mlp(g["pts"], grid, w1, w2, geo.hg)
+            fj = R.hashgrid_mlp(pj, grid, w1, w2, geo.hg)
             so, reg = self.material(g["pts"], f, fj, g["vd"], g["nrm"], env_id[b], reg_weight_n=total)
             regs.append(reg)
             canv = {"comp_rgb": AA.antialias(R.scatter_canvas(so["color"], g["pix"], H * W), g["aa"]).view(1, H, W, 3)}
@@ -380,14 +408,19 @@ class DreamMat:
         self.training_step_fused(b, global_views=V, total_pn_global=tot)
         return self.section_times()
 
-    def optimizer_step(self, grad_scale: float = 1.0):
+    def optimizer_step(self, grad_scale: float = 1.0, from_autograd: bool = False):
+        """Fused Adam on the flat buffer.  from_autograd: the gradients were produced by `loss.backward()` through the
+        autograd wrappers (forward() path) and are first collected from the leaves."""
+        if from_autograd:
+            self.geometry.grads_from_autograd()
         a = self.cfg.optimizer["args"]
         self.global_step += 1
         R.adam_step(self.geometry.params, self.geometry.grads, self.m, self.v, a["lr"], a["betas"][0], a["betas"][1],
                     a["eps"], self.global_step, grad_scale)
 
     def training_step_fused(self, batch: Dict[str, Any], global_views: Optional[int] = None,
-                            total_pn_global: Optional[int] = None, rng: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                            total_pn_global: Optional[int] = None, rng: Optional[dict] = None,
+                            apply_optimizer: bool = True) -> Dict[str, torch.Tensor]:
         """One SDS iteration (systems/dreammat.py:57-86 + backward + Adam) as an explicit kernel sequence.
 
         batch: output of the data mirror, already on the device (condition_map [B,H,W,22] fp32, cameras, env_id,
@@ -534,7 +567,8 @@ class DreamMat:
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(geo.grads, op=dist.ReduceOp.SUM)     # the single collective of the step (NVLink / NVSwitch)
-        self.optimizer_step()
+        if apply_optimizer:       # False: the host framework (Lightning) steps its own optimizer on the same flat gradient
+            self.optimizer_step()
         self._mark("render_bwd_adam")
         return {"loss": lam_sds * loss_sds.detach() + lam_reg * loss_reg, "loss_sds": loss_sds.detach(),
                 "loss_mat_reg": loss_reg, "comp_rgb": comp_rgb.detach(), "grad_norm": gout["grad_norm"]}

@@ -57,6 +57,72 @@ def load_safetensors(path: str) -> Dict[str, torch.Tensor]:
     return load_file(path)
 
 
+def unet_config_from_json(path: str, controlnet_json: str = None) -> UNetConfig:
+    """diffusers `unet/config.json` (and the ControlNet's `config.json` for the condition-embedding fields) -> UNetConfig.
+    Missing files / keys keep the SD-2.1-base defaults (controlnet_train/config.json:2, diffusers_train_controlnet.py:638)."""
+    import json
+    kw = {}
+    if path and os.path.exists(path):
+        with open(path) as f:
+            j = json.load(f)
+        heads = j.get("attention_head_dim", None)
+        if isinstance(heads, int):
+            heads = [heads] * len(j.get("block_out_channels", (320, 640, 1280, 1280)))
+        for src, dst in (("in_channels", "in_channels"), ("out_channels", "out_channels"), ("layers_per_block", "layers_per_block"),
+                         ("cross_attention_dim", "cross_attention_dim"), ("norm_num_groups", "norm_groups")):
+            if src in j:
+                kw[dst] = j[src]
+        if "block_out_channels" in j:
+            kw["block_out_channels"] = tuple(j["block_out_channels"])
+        if heads is not None:
+            kw["heads"] = tuple(heads)
+    if controlnet_json and os.path.exists(controlnet_json):
+        with open(controlnet_json) as f:
+            j = json.load(f)
+        if "conditioning_embedding_out_channels" in j:
+            kw["cond_embed_channels"] = tuple(j["conditioning_embedding_out_channels"])
+        if "conditioning_channels" in j:
+            kw["cond_channels"] = j["conditioning_channels"]
+    return UNetConfig(**kw)
+
+
+def vae_config_from_json(path: str) -> VAEConfig:
+    import json
+    kw = {}
+    if path and os.path.exists(path):
+        with open(path) as f:
+            j = json.load(f)
+        for src, dst in (("in_channels", "in_channels"), ("layers_per_block", "layers_per_block"), ("latent_channels", "latent_channels"),
+                         ("norm_num_groups", "norm_groups"), ("scaling_factor", "scaling_factor")):
+            if src in j:
+                kw[dst] = j[src]
+        if "block_out_channels" in j:
+            kw["block_out_channels"] = tuple(j["block_out_channels"])
+    return VAEConfig(**kw)
+
+
+_LEGACY_VAE_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+
+
+def normalize_vae_keys(w: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Published AutoencoderKL checkpoints (incl. stable-diffusion-2-1-base/vae) store the mid-block attention under the
+    deprecated names query / key / value / proj_attn, which diffusers renames at load time
+    (AutoencoderKL._convert_deprecated_attention_blocks); some also keep those projections as 1x1 conv weights
+    [C, C, 1, 1].  Bring both to the current names / shapes the graph in nets.VAEEncoder expects."""
+    out = {}
+    for k, v in w.items():
+        parts = k.split(".")
+        if "attentions" in parts:
+            i = parts.index("attentions")
+            if len(parts) > i + 2 and parts[i + 2] in _LEGACY_VAE_ATTN:
+                parts[i + 2] = _LEGACY_VAE_ATTN[parts[i + 2]]
+                k = ".".join(parts)
+            if k.endswith((".to_q.weight", ".to_k.weight", ".to_v.weight", ".to_out.0.weight")) and v.dim() == 4:
+                v = v.reshape(v.shape[0], v.shape[1])
+        out[k] = v
+    return out
+
+
 class _Init:
     """Seeded random tensors in diffusers shapes (variance-preserving scales so a 30-layer fp16 forward
     stays in range).  Device-side generation keeps 1.26 G parameters out of host RAM."""

@@ -145,7 +145,6 @@ def test_training_step_runs_through_autograd_wrappers():
     cams = FixCameraSet(DataConfig(width=res, height=res), torch.Generator().manual_seed(0))
     vid, eid = cams.collate(torch.Generator().manual_seed(1), 2)
     batch = {k: (x.to(dev) if torch.is_tensor(x) else x) for k, x in cams.cameras(vid).items()}
-    geo.grid.requires_grad_(True)
     out = ren(env_id=eid, view_id=vid, **batch)
     assert set(out) >= {"comp_rgb", "opacity", "comp_depth", "comp_normal", "albedo", "metalness", "roughness",
                         "specular_light", "diffuse_light", "specular_color", "diffuse_color", "loss_mat_reg"}
@@ -159,4 +158,16 @@ def test_training_step_runs_through_autograd_wrappers():
     from dreammat_b200.guidance import _SDSLoss
     loss = _SDSLoss.apply(lat, dlat, sums[0] / 2) + out["loss_mat_reg"]
     loss.backward()
-    assert geo.grid.grad is not None and torch.isfinite(geo.grid.grad).all() and float(geo.grid.grad.abs().sum()) > 0
+    # the gradients land on the autograd leaves that alias the flat parameter buffer -- hash grid AND both MLP matrices --
+    # and optimizer_step(from_autograd=True) consumes them (fused Adam on the flat buffer)
+    leaves = geo.autograd_leaves()
+    for leaf in leaves:
+        assert leaf.grad is not None and torch.isfinite(leaf.grad).all() and float(leaf.grad.abs().sum()) > 0
+    from dreammat_b200.system import DreamMat
+    sysm = DreamMat(None, geo, mat, ren, guid, pu, dev)
+    p_before = geo.params.clone()
+    g_w2 = leaves[2].grad.clone()
+    sysm.optimizer_step(from_autograd=True)
+    assert torch.equal(geo.dW2, g_w2) and all(leaf.grad is None for leaf in leaves)
+    moved = (geo.params != p_before)
+    assert bool(moved[:geo.n_grid].any()) and bool(moved[geo.n_grid:].all())     # every MLP weight gets a gradient
