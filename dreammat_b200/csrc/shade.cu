@@ -108,6 +108,7 @@ struct McParams {
     float *albedo, *roughness, *metalness, *spec_light, *diff_light, *spec_color, *diff_color;
     uint32_t* hit_bits;
     int skip_horizon;   // dm_tune knob
+    int frontier;       // dm_tune "mc_frontier": shared-origin traversal (see origin_frontier below)
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
@@ -137,11 +138,104 @@ __device__ __forceinline__ D3 spec_direction(const PixState& px, float phi0, flo
     return d;
 }
 
+// ---- shared-origin traversal.  All 328 occlusion rays of a pixel start (to 1e-5) at the same surface point p, so the
+// part of the BVH whose boxes CONTAIN p -- a connected piece T_p hanging off the root, ~2 x depth nodes -- passes the slab
+// test of every one of them.  One lane walks T_p once per pixel and leaves in shared memory
+//   * the leaves inside T_p (the triangles around p: every ray tests them), and
+//   * the FRONTIER: children of T_p nodes whose box does not contain p (box + child code).
+// Each ray then runs two warp-uniform loops (local triangles, frontier boxes: broadcast loads, all lanes busy, no stack)
+// and only descends, divergently, into the frontier subtrees its own slab test hit.  The set of boxes / triangles a ray
+// can reach is exactly that of a root traversal (a box containing the origin always passes slab2), so the any-hit result
+// is bit-identical; measured effect in profiles/r02_shade_frontier.md.
+constexpr int FR_MAX = 48;        // frontier entries per pixel (overflow -> plain root traversal for that pixel)
+constexpr int FR_LEAF_MAX = 12;   // leaves of T_p
+constexpr float FR_INSIDE = 3e-5f;  // p must sit this far inside a box to count as contained (ray origins are p + 1e-5 d, |d| = 1)
+struct FrontierList {
+    float box[FR_MAX][6];
+    int code[FR_MAX];
+    int leaf[FR_LEAF_MAX];
+    int nf, nl;                   // nf < 0: overflow
+};
+
+__device__ __forceinline__ void origin_frontier(const BvhView& bv, f3 p, FrontierList& F) {
+    int nf = 0, nl = 0, sp = 0;
+    bool ok = true;
+    int stk[40];
+    int cur = bv.root;
+    if (cur < 0) { F.leaf[0] = cur; F.nf = 0; F.nl = 1; return; }
+    auto child = [&](int code, float lx, float ly, float lz, float hx, float hy, float hz) {
+        const bool inside = p.x > lx + FR_INSIDE && p.x < hx - FR_INSIDE && p.y > ly + FR_INSIDE && p.y < hy - FR_INSIDE &&
+                            p.z > lz + FR_INSIDE && p.z < hz - FR_INSIDE;
+        if (inside) {
+            if (code < 0) { if (nl < FR_LEAF_MAX) F.leaf[nl++] = code; else ok = false; }
+            else { if (sp < 40) stk[sp++] = code; else ok = false; }
+        } else {
+            if (nf < FR_MAX) {
+                F.box[nf][0] = lx; F.box[nf][1] = ly; F.box[nf][2] = lz; F.box[nf][3] = hx; F.box[nf][4] = hy; F.box[nf][5] = hz;
+                F.code[nf] = code; ++nf;
+            } else ok = false;
+        }
+    };
+    while (ok) {
+        const float4* n = bv.nodes + (int64_t)cur * 4;
+        const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+        child(__float_as_int(n3.x), n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+        child(__float_as_int(n3.y), n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+        if (sp == 0) break;
+        cur = stk[--sp];
+    }
+    F.nf = ok ? nf : -1;
+    F.nl = nl;
+}
+
+// any-hit over the frontier subtrees selected by `mask` (bit i = F.code[i]); same node / leaf steps as bvh_trace<true>
+__device__ __forceinline__ bool anyhit_subtrees(const BvhView& bv, const FrontierList& F, unsigned long long mask, f3 o, f3 d,
+                                                f3 inv, f3 oi) {
+    int stack[DM_BVH_STACK];
+    int sp = 0, cur = 0;
+    bool alive = mask != 0ull;
+    if (alive) { const int i = __ffsll((long long)mask) - 1; mask &= mask - 1ull; cur = F.code[i]; }
+    while (alive) {
+        while (alive && cur >= 0) {
+            const float4* n = bv.nodes + (int64_t)cur * 4;
+            float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+            float tl, tr;
+            bool hl = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, inv, oi, DM_RT_MAX_DIST, tl);
+            bool hr = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, inv, oi, DM_RT_MAX_DIST, tr);
+            int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+            if (hl && hr) {
+                bool lfirst = tl <= tr;
+                if (sp < DM_BVH_STACK) stack[sp++] = lfirst ? cr : cl;
+                cur = lfirst ? cl : cr;
+            } else if (hl) cur = cl;
+            else if (hr) cur = cr;
+            else if (sp > 0) cur = stack[--sp];
+            else if (mask) { const int i = __ffsll((long long)mask) - 1; mask &= mask - 1ull; cur = F.code[i]; }
+            else alive = false;
+        }
+        if (!alive) break;
+        {
+            const int code = ~cur;
+            const int first = code >> 2, cnt = (code & 3) + 1;
+            for (int k = 0; k < cnt; ++k) {
+                const float4* tp = bv.tris + (int64_t)(first + k) * 3;
+                float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+                float u, v;
+                if (tri_hit_pre(o, d, A, B, C, u, v) < DM_RT_MAX_DIST) return true;
+            }
+        }
+        if (sp > 0) cur = stack[--sp];
+        else if (mask) { const int i = __ffsll((long long)mask) - 1; mask &= mask - 1ull; cur = F.code[i]; }
+        else break;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
     __shared__ PixState s_px[MC_WARPS];
-    __shared__ float s_reg[2];
+    __shared__ FrontierList s_fr[MC_WARPS];
     const int nd = P.cfg.n_diffuse, ns = P.cfg.n_specular, S = nd + ns;
     float* s_td = s_tab;
     float* s_ts = s_tab + 3 * nd;
@@ -156,11 +250,14 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
         s_ts[2 * i] = PI_F * 2.0f * P.tab_s[2 * i];  // phi = pi * 2 * az (:583)
         s_ts[2 * i + 1] = P.tab_s[2 * i + 1];
     }
-    if (threadIdx.x < 2) s_reg[threadIdx.x] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t pix = (int64_t)blockIdx.x * MC_WARPS + warp;
-    if (pix < P.n) {
+    float reg_kd_acc = 0.f, reg_ks_acc = 0.f;     // lane 0: this warp's share of the smoothness regulariser
+    // Persistent warps: warp w of the grid shades pixels w, w + W, w + 2W, ... (W = warps in the grid) with no block-level
+    // synchronisation after the table load, so a slow pixel delays only its own warp, not the seven others of its CTA
+    // (9 % of the stall samples of the one-CTA-per-8-pixels version sat in its final barrier: profiles/r02_shade_frontier.md).
+    for (int64_t pix = (int64_t)blockIdx.x * MC_WARPS + warp; pix < P.n; pix += (int64_t)gridDim.x * MC_WARPS) {
+        __syncwarp();
         // coalesced staging of the 19 per-pixel input floats through shared memory
         if (lane < 3) s_in[warp][lane] = P.pts[3 * pix + lane];
         else if (lane < 6) s_in[warp][lane] = P.normals[3 * pix + lane - 3];
@@ -184,8 +281,11 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
             px.xs[0] = xs.x; px.xs[1] = xs.y; px.xs[2] = xs.z; px.ys[0] = ys.x; px.ys[1] = ys.y; px.ys[2] = ys.z;
             px.a = a; px.NoV = NoV; px.g1v = g1.v; px.g1d = g1.d;
             px.rd = P.rand_d[pix] * PI_F * 2.0f; px.rs = P.rand_s[pix] * PI_F * 2.0f;
+            if (P.frontier) origin_frontier(P.bvh, p, s_fr[warp]);
         }
         __syncwarp();
+        const FrontierList& FR = s_fr[warp];
+        const bool use_frontier = P.frontier && FR.nf >= 0;
         const float kd_pdf = (float)nd / (float)(ns + nd), ks_pdf = (float)ns / (float)(ns + nd);
 
         float Ld[3] = {0, 0, 0}, Ls[3] = {0, 0, 0};
@@ -247,11 +347,37 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
             if (P.skip_horizon && spec && !P.spec_light && !P.hit_bits &&
                 (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f) continue;
             // ---- occlusion first (:490-507): occluded samples contribute nothing, skip their BRDF math
-            bool hit;
+            bool hit = false;
             {
                 f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
-                float bt, bu, bvv; int bid;
-                hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+                if (use_frontier) {
+                    // (1) the triangles around p: warp-uniform loop, broadcast loads
+                    for (int li = 0; li < FR.nl; ++li) {
+                        const int code = ~FR.leaf[li];
+                        const int first = code >> 2, cnt = (code & 3) + 1;
+                        for (int k = 0; k < cnt; ++k) {
+                            const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
+                            const float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+                            float u, v;
+                            if (!hit && tri_hit_pre(o, dv, A, B, C, u, v) < DM_RT_MAX_DIST) hit = true;
+                        }
+                    }
+                    if (!hit) {
+                        // (2) frontier boxes: warp-uniform loop over shared memory; (3) divergent descent into the hit ones
+                        const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
+                        const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+                        unsigned long long mask = 0ull;
+                        for (int i = 0; i < FR.nf; ++i) {
+                            float tn;
+                            if (slab2(FR.box[i][0], FR.box[i][1], FR.box[i][2], FR.box[i][3], FR.box[i][4], FR.box[i][5], inv, oi,
+                                      DM_RT_MAX_DIST, tn)) mask |= 1ull << i;
+                        }
+                        hit = anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi);
+                    }
+                } else {
+                    float bt, bu, bvv; int bid;
+                    hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+                }
             }
             if (P.hit_bits && hit) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
             if (hit) continue;
@@ -326,12 +452,14 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
             if (P.diff_light) st3(P.diff_light, pix, mk3(lin2srgb_f(Ld[0] * invd), lin2srgb_f(Ld[1] * invd), lin2srgb_f(Ld[2] * invd)));
             if (P.spec_color) st3(P.spec_color, pix, mk3(lin2srgb_f(specv[0]), lin2srgb_f(specv[1]), lin2srgb_f(specv[2])));
             if (P.diff_color) st3(P.diff_color, pix, mk3(lin2srgb_f(diffv[0]), lin2srgb_f(diffv[1]), lin2srgb_f(diffv[2])));
-            atomicAdd(&s_reg[0], reg_kd);
-            atomicAdd(&s_reg[1], reg_ks);
+            reg_kd_acc += reg_kd;
+            reg_ks_acc += reg_ks;
         }
     }
-    __syncthreads();
-    if (threadIdx.x < 2 && P.reg_sums) atomicAdd(P.reg_sums + threadIdx.x, s_reg[threadIdx.x]);
+    if (lane == 0 && P.reg_sums && (reg_kd_acc != 0.f || reg_ks_acc != 0.f)) {
+        atomicAdd(P.reg_sums, reg_kd_acc);
+        atomicAdd(P.reg_sums + 1, reg_ks_acc);
+    }
 }
 
 
@@ -532,12 +660,16 @@ __global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, flo
 }  // namespace
 
 static int g_mc_skip_horizon = 1;
+static int g_mc_frontier = 1;     // shared-origin frontier traversal (dm_tune "mc_frontier")
+static int g_mc_persistent = 1;   // persistent warps, grid = resident CTAs (dm_tune "mc_persistent"; 0 = one CTA per 8 pixels)
 extern int g_bvh_leaf_max;
 
 /* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
 extern "C" int dm_tune(const char* key, int value) {
     if (!key) return DM_EINVAL;
     if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
+    else if (!strcmp(key, "mc_frontier")) g_mc_frontier = value;
+    else if (!strcmp(key, "mc_persistent")) g_mc_persistent = value;
     else if (!strcmp(key, "pdl")) g_dm_pdl = value ? 1 : 0;
     else if (!strcmp(key, "bvh_leaf")) g_bvh_leaf_max = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(key, "mc_refill") || !strcmp(key, "mc_leaf_batch")) { /* retired experiment knobs */ }
@@ -564,6 +696,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.albedo = albedo; P.roughness = roughness; P.metalness = metalness; P.spec_light = spec_light;
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
     P.skip_horizon = g_mc_skip_horizon;
+    P.frontier = g_mc_frontier;
     // direction tables + one compacted sample-id list per warp
     size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float) +
                   (size_t)MC_WARPS * (cfg->n_diffuse + cfg->n_specular) * sizeof(uint16_t);
@@ -572,7 +705,18 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
         DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_configured = smem;
     }
-    shade_mc_kernel<<<(unsigned)dm_ceil_div(n, MC_WARPS), MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
+    int64_t blocks = dm_ceil_div(n, MC_WARPS);
+    if (g_mc_persistent) {
+        static int per_sm = 0;
+        if (!per_sm) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel, MC_WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError(); per_sm = 2;
+            }
+        }
+        const int64_t resident = (int64_t)DM_NUM_SMS * per_sm;
+        if (blocks > resident) blocks = resident;
+    }
+    shade_mc_kernel<<<(unsigned)blocks, MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

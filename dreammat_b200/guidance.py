@@ -247,9 +247,9 @@ class StableDiffusionLightGuidance:
         if self.use_controlnet and list(self.cfg.control_types) != ["light"]:
             # dreammat.yaml:62 selects ['light']; the annotator-based types need controlnet_aux (out of scope)
             raise ValueError(f"control_types {self.cfg.control_types}: only ['light'] is supported on this path")
-        self.unet = UNet(unet_weights, unet_cfg, device, dtype)
-        self.controlnet = ControlNet(controlnet_weights, unet_cfg, device, dtype) if self.use_controlnet else None
-        self.vae = VAEEncoder(vae_weights, vae_cfg, device, dtype)
+        self.unet = UNet(unet_weights, unet_cfg, device, self.weights_dtype)
+        self.controlnet = ControlNet(controlnet_weights, unet_cfg, device, self.weights_dtype) if self.use_controlnet else None
+        self.vae = VAEEncoder(vae_weights, vae_cfg, device, self.weights_dtype)
         self.num_train_timesteps = 1000
         self.alphas = alphas_cumprod().to(self.device)
         self.set_min_max_steps()

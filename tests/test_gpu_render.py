@@ -271,3 +271,38 @@ def test_resize_bilinear_matches_torch(ops):
         dy = torch.rand(ref.shape, generator=g)
         ref.backward(dy); y.backward(cu(dy))
         assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
+
+
+def test_frontier_traversal_is_bit_identical_to_root_traversal():
+    """The shared-origin frontier traversal (shade.cu: origin_frontier / anyhit_subtrees) visits exactly the boxes and
+    triangles a root traversal would: occlusion bits, colours and Jacobians must be IDENTICAL, persistent warps or not."""
+    import ctypes as C
+    from dreammat_b200 import render_ops as R
+    from dreammat_b200._cabi import MaterialCfg, check, lib, ptr, stream_ptr
+    sc = make_scene(res=64, subdiv=4, bump=0.25, seed=7)
+    dev = "cuda"
+    bvh = R.Bvh(sc["v"], sc["f"])
+    env = R.envmap_pack(sc["env"].to(dev))
+    cfg = MaterialCfg(0.0, 0.9, 0.01, 0.9, 200, 128)
+    tab_d, tab_s = R.direction_tables(200).to(dev), R.direction_tables(128).to(dev)
+    n = sc["pn"]
+    t = lambda x: x.to(dev).reshape(n, -1).contiguous()  # noqa: E731
+    pts, nrm, vd, f, fj = t(sc["pts"]), t(sc["nrm"]), t(sc["vd"]), t(sc["features"]), t(sc["features_jitter"])
+    rd, rs = t(sc["rand_d"]).view(-1), t(sc["rand_s"]).view(-1)
+    outs = []
+    try:
+        for fr, pe in ((0, 0), (1, 0), (1, 1), (0, 1)):
+            lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe)
+            color, jac, reg = torch.empty(n, 3, device=dev), torch.empty(n, 9, device=dev), torch.zeros(2, device=dev)
+            bits = torch.zeros(n, (328 + 31) // 32, device=dev, dtype=torch.int32)
+            check(lib().dm_shade_mc_fwd(C.byref(cfg), bvh.h, ptr(env), env.shape[0], env.shape[1], ptr(tab_d), ptr(tab_s), ptr(pts),
+                                        ptr(nrm), ptr(vd), ptr(f), ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg),
+                                        *([None] * 7), ptr(bits), None, stream_ptr()), "dm_shade_mc_fwd")
+            outs.append((color, jac, bits, reg))
+    finally:
+        lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_persistent", 1)
+    occ = int(sum(bin(int(x) & 0xffffffff).count("1") for x in outs[0][2].flatten()[:4096].tolist()))
+    assert occ > 0                      # the bumpy mesh self-occludes: the comparison is not vacuous
+    for color, jac, bits, reg in outs[1:]:
+        assert torch.equal(bits, outs[0][2]) and torch.equal(color, outs[0][0]) and torch.equal(jac, outs[0][1])
+        assert torch.allclose(reg, outs[0][3], rtol=1e-5)
