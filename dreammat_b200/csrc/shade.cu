@@ -95,7 +95,7 @@ struct PixelIn {
     float m[5], mj[5];
 };
 
-constexpr int MC_WARPS = 8;
+constexpr int MC_WARPS_MAX = 8;   // warps (= pixels in flight) per CTA: template parameter of shade_mc_kernel, dm_tune "mc_warps"
 
 struct McParams {
     dm_material_cfg cfg;
@@ -147,7 +147,7 @@ __device__ __forceinline__ D3 spec_direction(const PixState& px, float phi0, flo
 // and only descends, divergently, into the frontier subtrees its own slab test hit.  The set of boxes / triangles a ray
 // can reach is exactly that of a root traversal (a box containing the origin always passes slab2), so the any-hit result
 // is bit-identical; measured effect in profiles/r02_shade_frontier.md.
-constexpr int FR_MAX = 48;        // frontier entries per pixel (overflow -> plain root traversal for that pixel)
+constexpr int FR_MAX = 64;        // frontier entries per pixel = bits of the per-ray hit mask (overflow -> plain root traversal)
 constexpr int FR_LEAF_MAX = 12;   // leaves of T_p
 constexpr float FR_INSIDE = 3e-5f;  // p must sit this far inside a box to count as contained (ray origins are p + 1e-5 d, |d| = 1)
 struct FrontierList {
@@ -186,6 +186,46 @@ __device__ __forceinline__ void origin_frontier(const BvhView& bv, f3 p, Frontie
     }
     F.nf = ok ? nf : -1;
     F.nl = nl;
+}
+
+// Frontier refinement (whole warp).  The warp-uniform slab loop over the frontier is ~20 instructions per box with all
+// lanes busy; a divergent node visit costs ~60 at a third of the lanes.  So the frontier is grown towards FR_MAX entries by
+// repeatedly replacing the internal node that subtends the largest solid angle from p (surface area / squared distance: the
+// box most rays hit, i.e. the one whose false positives cost most) by its two children.  Purely a re-arrangement of which
+// box tests run coherently: the reachable set of triangles is unchanged.
+__device__ __forceinline__ void refine_frontier(const BvhView& bv, f3 p, FrontierList& F, int lane, int target) {
+    int nf = F.nf;
+    if (nf < 0) return;
+    while (nf < target) {
+        float best = -1.0f; int best_i = -1;
+        for (int i = lane; i < nf; i += 32) {
+            if (F.code[i] < 0) continue;                       // leaves cannot be opened
+            const float* b = F.box[i];
+            const float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+            const float dx = fmaxf(fmaxf(b[0] - p.x, p.x - b[3]), 0.f), dy = fmaxf(fmaxf(b[1] - p.y, p.y - b[4]), 0.f),
+                        dz = fmaxf(fmaxf(b[2] - p.z, p.z - b[5]), 0.f);
+            const float m = (ex * ey + ey * ez + ez * ex) / (dx * dx + dy * dy + dz * dz + 1e-6f);
+            if (m > best) { best = m; best_i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ob > best || (ob == best && oi >= 0 && (best_i < 0 || oi < best_i))) { best = ob; best_i = oi; }
+        }
+        if (best_i < 0) break;                                 // only leaves left
+        if (lane == 0) {
+            const float4* n = bv.nodes + (int64_t)F.code[best_i] * 4;
+            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+            float* a = F.box[best_i]; float* c = F.box[nf];
+            a[0] = n0.x; a[1] = n0.y; a[2] = n0.z; a[3] = n0.w; a[4] = n1.x; a[5] = n1.y; F.code[best_i] = __float_as_int(n3.x);
+            c[0] = n1.z; c[1] = n1.w; c[2] = n2.x; c[3] = n2.y; c[4] = n2.z; c[5] = n2.w; F.code[nf] = __float_as_int(n3.y);
+        }
+        ++nf;
+        __syncwarp();
+    }
+    if (lane == 0) F.nf = nf;
+    __syncwarp();
 }
 
 // any-hit over the frontier subtrees selected by `mask` (bit i = F.code[i]); same node / leaf steps as bvh_trace<true>
@@ -231,7 +271,8 @@ __device__ __forceinline__ bool anyhit_subtrees(const BvhView& bv, const Frontie
     return false;
 }
 
-__global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) {
+template <int MC_WARPS>
+__global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
     __shared__ PixState s_px[MC_WARPS];
@@ -284,6 +325,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 3) shade_mc_kernel(McParams P) 
             if (P.frontier) origin_frontier(P.bvh, p, s_fr[warp]);
         }
         __syncwarp();
+        if (P.frontier > 1) refine_frontier(P.bvh, mk3(px.p[0], px.p[1], px.p[2]), s_fr[warp], lane, P.frontier < FR_MAX ? P.frontier : FR_MAX);
         const FrontierList& FR = s_fr[warp];
         const bool use_frontier = P.frontier && FR.nf >= 0;
         const float kd_pdf = (float)nd / (float)(ns + nd), ks_pdf = (float)ns / (float)(ns + nd);
@@ -660,8 +702,10 @@ __global__ void envmap_pack_kernel(const float* __restrict__ rgb, int64_t n, flo
 }  // namespace
 
 static int g_mc_skip_horizon = 1;
-static int g_mc_frontier = 1;     // shared-origin frontier traversal (dm_tune "mc_frontier")
-static int g_mc_persistent = 1;   // persistent warps, grid = resident CTAs (dm_tune "mc_persistent"; 0 = one CTA per 8 pixels)
+static int g_mc_frontier = 1;     // dm_tune "mc_frontier": 0 root traversal | 1 shared-origin frontier | N > 1 frontier refined to N boxes (<= 64)
+static int g_mc_persistent = 0;   // dm_tune "mc_persistent": 1 = persistent warps with a static pixel interleave (measured slower:
+                                  // per-pixel cost varies ~1:5, the hardware's CTA scheduler balances better), 0 = one CTA per MC_WARPS pixels
+static int g_mc_warps = 8;        // dm_tune "mc_warps": pixels (warps) per CTA, 1 | 2 | 4 | 8
 extern int g_bvh_leaf_max;
 
 /* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
@@ -670,12 +714,18 @@ extern "C" int dm_tune(const char* key, int value) {
     if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
     else if (!strcmp(key, "mc_frontier")) g_mc_frontier = value;
     else if (!strcmp(key, "mc_persistent")) g_mc_persistent = value;
+    else if (!strcmp(key, "mc_warps")) {
+        if (value != 1 && value != 2 && value != 4 && value != 8) { dm_set_error("dm_tune mc_warps: 1, 2, 4 or 8"); return DM_EINVAL; }
+        g_mc_warps = value;
+    }
     else if (!strcmp(key, "pdl")) g_dm_pdl = value ? 1 : 0;
     else if (!strcmp(key, "bvh_leaf")) g_bvh_leaf_max = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(key, "mc_refill") || !strcmp(key, "mc_leaf_batch")) { /* retired experiment knobs */ }
     else { dm_set_error("dm_tune: unknown key %s", key); return DM_EINVAL; }
     return DM_OK;
 }
+
+static int launch_mc(const McParams& P, cudaStream_t st);
 
 extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, const float* env_rgba, int envH, int envW,
                                const float* tab_d, const float* tab_s, const float* pts, const float* normals,
@@ -697,26 +747,45 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
     P.skip_horizon = g_mc_skip_horizon;
     P.frontier = g_mc_frontier;
+    return launch_mc(P, (cudaStream_t)stream);
+}
+
+namespace {
+template <int W>
+int launch_mc_w(const McParams& P, cudaStream_t st) {
     // direction tables + one compacted sample-id list per warp
-    size_t smem = (size_t)(3 * cfg->n_diffuse + 2 * cfg->n_specular) * sizeof(float) +
-                  (size_t)MC_WARPS * (cfg->n_diffuse + cfg->n_specular) * sizeof(uint16_t);
-    static size_t smem_configured = 48 * 1024;
+    const size_t smem = (size_t)(3 * P.cfg.n_diffuse + 2 * P.cfg.n_specular) * sizeof(float) +
+                        (size_t)W * (P.cfg.n_diffuse + P.cfg.n_specular) * sizeof(uint16_t);
+    static size_t smem_configured = 0;
     if (smem > smem_configured) {
-        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_configured = smem;
     }
-    int64_t blocks = dm_ceil_div(n, MC_WARPS);
+    int64_t blocks = dm_ceil_div(P.n, W);
     if (g_mc_persistent) {
         static int per_sm = 0;
         if (!per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel, MC_WARPS * 32, smem) != cudaSuccess || per_sm < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel<W>, W * 32, smem) != cudaSuccess || per_sm < 1) {
                 cudaGetLastError(); per_sm = 2;
             }
         }
         const int64_t resident = (int64_t)DM_NUM_SMS * per_sm;
         if (blocks > resident) blocks = resident;
     }
-    shade_mc_kernel<<<(unsigned)blocks, MC_WARPS * 32, smem, (cudaStream_t)stream>>>(P);
+    shade_mc_kernel<W><<<(unsigned)blocks, W * 32, smem, st>>>(P);
+    return DM_OK;
+}
+}  // namespace
+
+static int launch_mc(const McParams& P, cudaStream_t st) {
+    int rc;
+    switch (g_mc_warps) {
+        case 1: rc = launch_mc_w<1>(P, st); break;
+        case 2: rc = launch_mc_w<2>(P, st); break;
+        case 4: rc = launch_mc_w<4>(P, st); break;
+        default: rc = launch_mc_w<8>(P, st); break;
+    }
+    if (rc) return rc;
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

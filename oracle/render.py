@@ -306,7 +306,7 @@ def shade_raytracing(pts, normals, view_dirs, light, metallic, roughness, albedo
     pts_ = pts.unsqueeze(1).repeat(1, sn, 1)
     o = pts_.reshape(-1, 3) + directions.reshape(-1, 3).detach() * 1e-5
     hit = trace_fn(o, directions.reshape(-1, 3).detach()).reshape(-1, sn)
-    lights = torch.zeros(pts.shape[0], sn, 3)
+    lights = torch.zeros(pts.shape[0], sn, 3, dtype=light.dtype)
     miss = ~hit
     if miss.any():
         lights[miss] = envmap_lookup(light, directions.detach()[miss])

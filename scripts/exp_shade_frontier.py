@@ -22,9 +22,9 @@ for vid in (3, 40):
     f = torch.randn(n, 5, device=dev, generator=gen); fj = torch.randn(n, 5, device=dev, generator=gen)
     rd, rs = torch.rand(n, device=dev, generator=gen), torch.rand(n, device=dev, generator=gen)
     ref = None
-    for (fr, pe, leaf) in ((0, 0, 4), (0, 1, 4), (1, 0, 4), (1, 1, 4), (1, 1, 2), (1, 1, 1)):
-        lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe); lib().dm_tune(b"bvh_leaf", leaf)
-        bvh = R.Bvh(mesh[0], mesh[1])
+    bvh = R.Bvh(mesh[0], mesh[1])
+    for (fr, warps) in ((0, 8), (1, 8), (32, 8), (48, 8), (64, 8), (0, 4), (1, 4), (48, 4), (64, 4), (1, 2), (48, 2), (64, 2), (1, 1), (48, 1), (64, 1)):
+        lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_warps", warps)
         def run():
             return R.shade_mc(f, fj, g["pts"], g["nrm"], g["vd"], rd, rs, mat.mc_cfg, bvh, mat.light[0], mat.tab_d,
                               mat.tab_s, want_aux=False)[0]
@@ -36,6 +36,5 @@ for vid in (3, 40):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         if ref is None: ref = col.clone()
-        same = bool(torch.equal(col, ref)) if leaf == 4 else float((col - ref).abs().max())
-        print(f"view {vid} pn={n} frontier={fr} persistent={pe} leaf<={leaf}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  identical_to_first={same}")
-lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_persistent", 1); lib().dm_tune(b"bvh_leaf", 4)
+        print(f"view {vid} pn={n} frontier={fr:2d} warps/CTA={warps}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  identical_to_first={bool(torch.equal(col, ref))}")
+lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_warps", 8)

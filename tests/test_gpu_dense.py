@@ -236,34 +236,59 @@ def test_guidance_step_matches_oracle(small):
 
 
 def test_fused_csd_epilogue_matches_unfused(small):
-    """J1: conv_out with the CSD combination fused into its epilogue (dm_conv2d_csd) against conv_out + layout change +
-    dm_sds_grad on the same UNet activations: the noise predictions must be identical and grad / dlatents / the ten
-    logged sums equal to fp32 reduction order."""
-    from dreammat_b200.guidance import PromptProcessorOutput, StableDiffusionLightGuidance
-    ucfg, vcfg, wu, wc, wv = small
-    g = torch.Generator().manual_seed(9)
-    Dm = ucfg.cross_attention_dim
-    for (B, hw) in ((2, 16), (4, 8), (1, 32)):
-        lat = torch.randn(B, 4, hw, hw, generator=g).cuda()
-        noise = torch.randn(B, 4, hw, hw, generator=g).cuda()
-        cond = torch.rand(B, 8 * hw, 8 * hw, 22, generator=g).cuda()
-        ctx3 = torch.randn(3 * B, 77, Dm, generator=g)
-        t = torch.randint(20, 981, (B,), generator=g).cuda()
-        cfg = dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05, uncond_scale=-0.7,
-                   null_scale=-0.2, noise_scale=0.1)
-        guid = StableDiffusionLightGuidance(cfg, ucfg, vcfg, wu, wc, wv)
-        guid.keep_debug = True
-        from dreammat_b200 import dense_ops as D
+    """J1: conv_out with the CSD combination fused into its epilogue (dm_conv2d_csd).
+    (1) op level, same input activation: the noise predictions it emits equal conv_out + layout change (D.conv2d +
+        nhwc_to_nchw) up to fp32 summation order before the fp16 rounding, and grad / dlatents / the ten logged sums equal
+        the closed form of dreammat_guidance.py:475-495,584-594 applied to those predictions (fp32 reduction order);
+    (2) through the guidance object: fused and unfused evaluation agree within the fp16 run-to-run noise of the network
+        (split-K and GroupNorm use fp32 atomics, so two runs of the same UNet differ by ~1e-3 themselves: measured, printed)."""
+    import torch.nn.functional as F
+    from dreammat_b200 import dense_ops as D
+    from dreammat_b200.guidance import StableDiffusionLightGuidance
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rn = lambda *s_: torch.randn(*s_, device="cuda", generator=g)  # noqa: E731
+    for (B, hw, Cin) in ((2, 16, 64), (4, 8, 128), (1, 32, 320), (8, 64, 320)):
         assert D.csd_supported(torch.float16, B, hw, hw)
-        guid.fuse_csd = True
-        g1, d1, s1 = guid.compute_grad_sds(lat, cond, ctx3, t, noise)
-        e1 = guid.debug["eps"].clone()
-        guid.fuse_csd = False
-        g0, d0, s0 = guid.compute_grad_sds(lat, cond, ctx3, t, noise)
-        e0 = guid.debug["eps"]
-        errs = dict(eps=rel(e1, e0), grad=rel(g1, g0), dlat=rel(d1, d0), sums=float(((s1 - s0).abs() / s0.abs().clamp_min(1e-20)).max()))
-        print(f"\nfused CSD epilogue B={B} {hw}x{hw}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
-        assert errs["eps"] == 0.0 and errs["grad"] < 1e-6 and errs["dlat"] < 1e-6 and errs["sums"] < 1e-5, errs
+        x = rn(3 * B, hw, hw, Cin).half()
+        w4 = (rn(4, Cin, 3, 3) / (3 * Cin ** 0.5)).half()
+        wg = D.conv_weight_to_gemm(w4)
+        bias = (rn(4) * 0.1).half()
+        noise, w1mac = rn(B, 4, hw, hw), torch.rand(B, device="cuda", generator=g)
+        coef = torch.tensor([1.05, -0.7, -0.2, 0.1, 0.37], device="cuda")
+        grad, dlat, sums = torch.empty_like(noise), torch.empty_like(noise), torch.zeros(10, device="cuda")
+        eps = torch.empty(3, B, 4, hw, hw, device="cuda")
+        D.conv2d_csd(x, wg, bias, noise, w1mac, coef, grad, dlat, sums, eps)
+        out = torch.empty(3 * B, hw, hw, 8, device="cuda", dtype=torch.float16)
+        D.conv2d(x, wg, 3, bias=bias, out=out[..., :4])
+        eps_ref = D.nhwc_to_nchw_f32(out, 4).view(3, B, 4, hw, hw)
+        et, eu, en = eps[0], eps[1], eps[2]
+        gref = torch.nan_to_num(w1mac.view(-1, 1, 1, 1) * (1.05 * et - 0.7 * eu - 0.2 * en + 0.1 * noise))
+        sref = torch.stack([0.5 * (gref ** 2).sum(), (gref ** 2).sum(), ((eu - noise) ** 2).sum(), ((et - noise) ** 2).sum(),
+                            ((et - eu) ** 2).sum(), ((et - en) ** 2).sum(), ((en - eu) ** 2).sum(), (noise ** 2).sum(), (eu ** 2).sum(),
+                            (et ** 2).sum()])
+        errs = dict(eps=rel(eps, eps_ref), grad=rel(grad, gref), dlat=rel(dlat, gref * 0.37),
+                    sums=float(((sums - sref).abs() / sref.abs().clamp_min(1e-20)).max()))
+        print(f"\nfused CSD epilogue op B={B} {hw}x{hw} Cin={Cin}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+        assert errs["eps"] < 1e-4 and errs["grad"] < 1e-6 and errs["dlat"] < 1e-6 and errs["sums"] < 1e-5, errs
+    ucfg, vcfg, wu, wc, wv = small
+    gc = torch.Generator().manual_seed(9)
+    B, hw, Dm = 2, 16, ucfg.cross_attention_dim
+    lat, noise = torch.randn(B, 4, hw, hw, generator=gc).cuda(), torch.randn(B, 4, hw, hw, generator=gc).cuda()
+    cond, ctx3 = torch.rand(B, 8 * hw, 8 * hw, 22, generator=gc).cuda(), torch.randn(3 * B, 77, Dm, generator=gc)
+    t = torch.randint(20, 981, (B,), generator=gc).cuda()
+    guid = StableDiffusionLightGuidance(dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05,
+                                             uncond_scale=-0.7, null_scale=-0.2, noise_scale=0.1), ucfg, vcfg, wu, wc, wv)
+    guid.keep_debug = True
+    runs = []
+    for fuse in (True, False, False):
+        guid.fuse_csd = fuse
+        g_, d_, s_ = guid.compute_grad_sds(lat, cond, ctx3, t, noise)
+        runs.append((guid.debug["eps"].clone(), g_.clone(), s_.clone()))
+    noise_floor = rel(runs[1][1], runs[2][1])          # unfused vs unfused: the network's own run-to-run noise
+    e_fused = rel(runs[0][1], runs[1][1])
+    print(f"fused vs unfused through the guidance: sds-grad {e_fused:.1e}, eps {rel(runs[0][0], runs[1][0]):.1e}; "
+          f"unfused run-to-run {noise_floor:.1e}")
+    assert e_fused < max(3 * noise_floor, 2e-2)
 
 
 @pytest.mark.slow

@@ -273,6 +273,9 @@ def test_resize_bilinear_matches_torch(ops):
         assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
 
 
+DEFAULT_FRONTIER, DEFAULT_WARPS = 1, 8     # library defaults (csrc/shade.cu g_mc_frontier / g_mc_warps)
+
+
 def test_frontier_traversal_is_bit_identical_to_root_traversal():
     """The shared-origin frontier traversal (shade.cu: origin_frontier / anyhit_subtrees) visits exactly the boxes and
     triangles a root traversal would: occlusion bits, colours and Jacobians must be IDENTICAL, persistent warps or not."""
@@ -291,8 +294,8 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
     rd, rs = t(sc["rand_d"]).view(-1), t(sc["rand_s"]).view(-1)
     outs = []
     try:
-        for fr, pe in ((0, 0), (1, 0), (1, 1), (0, 1)):
-            lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe)
+        for fr, pe, wp in ((0, 0, 8), (1, 0, 8), (1, 1, 8), (0, 1, 4), (48, 0, 2), (64, 0, 1), (64, 0, 8)):
+            lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe); lib().dm_tune(b"mc_warps", wp)
             color, jac, reg = torch.empty(n, 3, device=dev), torch.empty(n, 9, device=dev), torch.zeros(2, device=dev)
             bits = torch.zeros(n, (328 + 31) // 32, device=dev, dtype=torch.int32)
             check(lib().dm_shade_mc_fwd(C.byref(cfg), bvh.h, ptr(env), env.shape[0], env.shape[1], ptr(tab_d), ptr(tab_s), ptr(pts),
@@ -300,7 +303,7 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
                                         *([None] * 7), ptr(bits), None, stream_ptr()), "dm_shade_mc_fwd")
             outs.append((color, jac, bits, reg))
     finally:
-        lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_persistent", 1)
+        lib().dm_tune(b"mc_frontier", DEFAULT_FRONTIER); lib().dm_tune(b"mc_persistent", 0); lib().dm_tune(b"mc_warps", DEFAULT_WARPS)
     occ = int(sum(bin(int(x) & 0xffffffff).count("1") for x in outs[0][2].flatten()[:4096].tolist()))
     assert occ > 0                      # the bumpy mesh self-occludes: the comparison is not vacuous
     for color, jac, bits, reg in outs[1:]:
