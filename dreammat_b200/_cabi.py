@@ -92,6 +92,10 @@ SIGNATURES = {
     "dm_timestep_embedding": (C.c_int, [C.c_int, P, C.c_int, C.c_int, P, P]),
     "dm_silu": (C.c_int, [C.c_int, P, I64, P, P]),
     "dm_attention": (C.c_int, [C.c_int, P, I64, I64, P, P, I64, I64, P, I64, I64] + [C.c_int] * 5 + [F, P]),
+    "dm_cond_gather": (C.c_int, [C.c_int, P, P, P, C.c_int, I64, P, P, C.c_int, C.c_int, P, P]),
+    "dm_envlight_latlong_to_cube": (C.c_int, [P, C.c_int, C.c_int, F, C.c_int, P, P]),
+    "dm_envlight_downsample": (C.c_int, [P, C.c_int, P, P]),
+    "dm_envlight_filter": (C.c_int, [P, C.c_int, C.c_int, F, F, P, P]),
     "dm_conv2d_csd": (C.c_int, [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, P]),
     "dm_hp_split": (C.c_int, [P, I64, C.c_int, I64, C.c_int, P, P]),
     "dm_hp_epilogue": (C.c_int, [P, I64, C.c_int, I64, P, P, I64, I64, P]),

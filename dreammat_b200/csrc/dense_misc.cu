@@ -505,6 +505,37 @@ __global__ void __launch_bounds__(256) pad_convert_kernel(const float* __restric
         *reinterpret_cast<uint4*>(y + r * cpad + c0) = o;
     }
 }
+// N1: the pre-rendered condition maps stay on the device as the bytes the PNG decode produced
+// (data/uncond.py:532-582): depth fp32 [V, HW], normal u8 [V, HW, 3], light u8 [V, E, HW, 18].  One pass gathers the
+// (view, env) pairs of the batch, de-quantises (x / 255, the reference's arithmetic) and writes the channel-padded
+// ControlNet condition [B, HW, cpad] in the storage dtype: channel order depth | normal | 6 x RGB light (:581-582,:802).
+template <typename T>
+__global__ void __launch_bounds__(256) cond_gather_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ normal,
+                                                          const uint8_t* __restrict__ light, int E, int64_t HW,
+                                                          const int32_t* __restrict__ view_ids, const int32_t* __restrict__ env_ids,
+                                                          int B, int cpad, T* __restrict__ out) {
+    const int vpr = cpad >> 3;
+    const int64_t n = (int64_t)B * HW * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % vpr) * 8; const int64_t r = i / vpr;
+        const int64_t px = r % HW; const int b = (int)(r / HW);
+        const int v = view_ids[b], e = env_ids[b];
+        const uint8_t* nr = normal + ((int64_t)v * HW + px) * 3;
+        const uint8_t* lt = light + (((int64_t)v * E + e) * HW + px) * 18;
+        uint4 o; T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            float f = 0.f;
+            if (c == 0) f = depth[(int64_t)v * HW + px];
+            else if (c < 4) f = (float)nr[c - 1] / 255.0f;
+            else if (c < 22) f = (float)lt[c - 4] / 255.0f;
+            oh[k] = H<T>::t(f);
+        }
+        *reinterpret_cast<uint4*>(out + r * cpad + c0) = o;
+    }
+}
+
 // T [rows, ld] (first cout channels) -> fp32 [rows, cout] * scale
 template <typename T>
 __global__ void __launch_bounds__(256) unpad_convert_kernel(const T* __restrict__ x, int64_t rows, int ld, int cout,
@@ -741,6 +772,17 @@ extern "C" int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, i
     if (bf16 == 2) return hp_pad_convert(x, rows, cin, cpad, scale, shift, (float*)y, stream);
     DM_REQUIRE(x && y && cpad >= cin && cpad % 8 == 0, "bad args (cpad must be a multiple of 8)");
     DM_DISPATCH_T(bf16, pad_convert_kernel<T><<<grid_for(rows * (cpad / 8)), 256, 0, (cudaStream_t)stream>>>(x, rows, cin, cpad, scale, shift, (T*)y));
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+}
+
+extern "C" int dm_cond_gather(int bf16, const float* depth, const uint8_t* normal, const uint8_t* light, int n_env, int64_t HW,
+                              const int32_t* view_ids, const int32_t* env_ids, int B, int cpad, void* out, void* stream) {
+    DM_REQUIRE(bf16 == 0 || bf16 == 1, "16-bit storage (the fp32 mode takes the float condition map through dm_pad_convert)");
+    DM_REQUIRE(depth && normal && light && view_ids && env_ids && out && cpad >= 22 && cpad % 8 == 0 && n_env > 0, "bad args");
+    if (B == 0 || HW == 0) return DM_OK;
+    DM_DISPATCH_T(bf16, cond_gather_kernel<T><<<grid_for((int64_t)B * HW * (cpad / 8)), 256, 0, (cudaStream_t)stream>>>(
+                            depth, normal, light, n_env, HW, view_ids, env_ids, B, cpad, (T*)out));
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

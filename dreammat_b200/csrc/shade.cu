@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
 struct SsParams {
     dm_material_cfg cfg;
     const float* lut; int lut_res;
-    const float* dcube; int dres;
+    const float* dcube; int dres; int dcube_smem;
     const float* mips[8]; int n_mips; int res0;
     const float *normals, *viewdirs, *features, *features_jitter;
     int64_t n;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void dir_cube(f3 d, int& face, float& s, float& t) {
     s = sv / ma; t = tv / ma;
 }
 // seamless texel fetch (edge texels come from the neighbouring face, corner texels are dropped)
-__device__ __forceinline__ bool cube_texel(const float* __restrict__ cube, int res, int face, int ix, int iy, f3& val) {
+__device__ __forceinline__ bool cube_texel(const float* cube, int res, int face, int ix, int iy, f3& val) {
     bool inx = ix >= 0 && ix < res, iny = iy >= 0 && iy < res;
     if (!(inx || iny)) { val = mk3(0, 0, 0); return false; }
     if (!(inx && iny)) {
@@ -550,11 +550,11 @@ __device__ __forceinline__ bool cube_texel(const float* __restrict__ cube, int r
         ix = min(max((int)floorf((s2 + 1.0f) * 0.5f * (float)res), 0), res - 1);
         iy = min(max((int)floorf((t2 + 1.0f) * 0.5f * (float)res), 0), res - 1);
     }
-    const float* p = cube + (((int64_t)face * res + iy) * res + ix) * 3;
-    val = mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+    const float* p = cube + (((int64_t)face * res + iy) * res + ix) * 3;   // global (L1-cached) or shared memory
+    val = mk3(p[0], p[1], p[2]);
     return true;
 }
-__device__ __forceinline__ f3 cube_linear(const float* __restrict__ cube, int res, f3 d) {
+__device__ __forceinline__ f3 cube_linear(const float* cube, int res, f3 d) {
     int face; float s, t;
     dir_cube(d, face, s, t);
     float x = (s + 1.0f) * 0.5f * (float)res - 0.5f, y = (t + 1.0f) * 0.5f * (float)res - 0.5f;
@@ -572,20 +572,71 @@ __device__ __forceinline__ f3 cube_linear(const float* __restrict__ cube, int re
     return acc * (1.0f / ws);
 }
 
-__global__ void __launch_bounds__(128) shade_splitsum_kernel(SsParams P) {
+// HBM-bound kernel (124 B read+written per covered pixel forward, 200 B with the backward):
+//   * persistent CTAs (grid = a multiple of the SM count) walk chunks of 128 pixels;
+//   * the chunk's G-buffer rows (normal, view direction: 3 floats; features, jittered features: 5 floats) are dense
+//     arrays, so the CTA moves them as 16-byte vectors (float4) into shared memory -- fully coalesced whatever the row
+//     length -- and the colour / Jacobian rows leave the same way;
+//   * the diffuse irradiance cube (6 x 16 x 16 x 3 floats = 18 KB) is staged in shared memory once per CTA; the specular
+//     mips and the 512 KB FG LUT stay L1 / L2-resident (texture-like gathers, excluded from the algorithmic bytes).
+constexpr int SS_CHUNK = 128;
+__device__ __forceinline__ void ss_stage_in(const float* __restrict__ g, float* s, int64_t row0, int rows, int per, int tid) {
+    const float* base = g + row0 * per;
+    const int total = rows * per;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const int nv = total >> 2;
+        for (int i = tid; i < nv; i += SS_CHUNK) reinterpret_cast<float4*>(s)[i] = __ldg(reinterpret_cast<const float4*>(base) + i);
+        for (int i = (nv << 2) + tid; i < total; i += SS_CHUNK) s[i] = __ldg(base + i);
+    } else {
+        for (int i = tid; i < total; i += SS_CHUNK) s[i] = __ldg(base + i);
+    }
+}
+__device__ __forceinline__ void ss_stage_out(float* __restrict__ g, const float* s, int64_t row0, int rows, int per, int tid) {
+    float* base = g + row0 * per;
+    const int total = rows * per;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const int nv = total >> 2;
+        for (int i = tid; i < nv; i += SS_CHUNK) reinterpret_cast<float4*>(base)[i] = reinterpret_cast<const float4*>(s)[i];
+        for (int i = (nv << 2) + tid; i < total; i += SS_CHUNK) base[i] = s[i];
+    } else {
+        for (int i = tid; i < total; i += SS_CHUNK) base[i] = s[i];
+    }
+}
+
+__global__ void __launch_bounds__(SS_CHUNK) shade_splitsum_kernel(SsParams P) {
     __shared__ float s_reg[2];
+    __shared__ __align__(16) float s_n[SS_CHUNK * 3], s_v[SS_CHUNK * 3], s_f[SS_CHUNK * 5], s_fj[SS_CHUNK * 5];
+    __shared__ __align__(16) float s_col[SS_CHUNK * 3], s_jac[SS_CHUNK * 9];
+    extern __shared__ float s_dcube[];      // [6 * dres * dres * 3] when P.dcube_smem, else unused
     if (threadIdx.x < 2) s_reg[threadIdx.x] = 0.f;
+    const float* dcube = P.dcube;
+    if (P.dcube_smem) {
+        const int nd = 6 * P.dres * P.dres * 3;
+        for (int i = threadIdx.x; i < nd; i += SS_CHUNK) s_dcube[i] = __ldg(P.dcube + i);
+        dcube = s_dcube;
+    }
     __syncthreads();
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float reg_kd = 0.f, reg_ks = 0.f;
-    if (pix < P.n) {
-        f3 n = ld3(P.normals, pix), v = ld3(P.viewdirs, pix);
+    const int64_t n_chunks = (P.n + SS_CHUNK - 1) / SS_CHUNK;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t row0 = chunk * SS_CHUNK;
+        const int rows = (int)((P.n - row0) < SS_CHUNK ? (P.n - row0) : SS_CHUNK);
+        __syncthreads();                      // previous chunk's staged outputs have been written out
+        ss_stage_in(P.normals, s_n, row0, rows, 3, threadIdx.x);
+        ss_stage_in(P.viewdirs, s_v, row0, rows, 3, threadIdx.x);
+        ss_stage_in(P.features, s_f, row0, rows, 5, threadIdx.x);
+        ss_stage_in(P.features_jitter, s_fj, row0, rows, 5, threadIdx.x);
+        __syncthreads();
+        const int lp = threadIdx.x;
+        const int64_t pix = row0 + lp;
+        if (lp < rows) {
+        f3 n = mk3(s_n[3 * lp], s_n[3 * lp + 1], s_n[3 * lp + 2]), v = mk3(s_v[3 * lp], s_v[3 * lp + 1], s_v[3 * lp + 2]);
         float m[5], mj[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(P.features[5 * pix + k]); mj[k] = sigmoidf_(P.features_jitter[5 * pix + k]); }
+        for (int k = 0; k < 5; ++k) { m[k] = sigmoidf_(s_f[5 * lp + k]); mj[k] = sigmoidf_(s_fj[5 * lp + k]); }
         float k0 = fabsf(m[0] - mj[0]), k1 = fabsf(m[1] - mj[1]), k2 = fabsf(m[2] - mj[2]);
-        reg_kd = ((k0 + k1 + k2) / 3.0f) * k2;
-        reg_ks = fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
+        reg_kd += ((k0 + k1 + k2) / 3.0f) * k2;
+        reg_ks += fabsf(m[3] - mj[3]) * fabsf(m[4] - mj[4]);
         float alb[3] = {fminf(fmaxf(m[0], 0.f), 1.f), fminf(fmaxf(m[1], 0.f), 1.f), fminf(fmaxf(m[2], 0.f), 1.f)};
         float met = m[3] * (P.cfg.max_metallic - P.cfg.min_metallic) + P.cfg.min_metallic;
         float rough = m[4] * (P.cfg.max_roughness - P.cfg.min_roughness) + P.cfg.min_roughness;
@@ -608,7 +659,7 @@ __global__ void __launch_bounds__(128) shade_splitsum_kernel(SsParams P) {
             bool rin = rough >= 0.f && rough <= 1.f;
             dfg0 = rin ? (t1x - t0x) * R : 0.f; dfg1 = rin ? (t1y - t0y) * R : 0.f;
         }
-        f3 dl = cube_linear(P.dcube, P.dres, n);
+        f3 dl = cube_linear(dcube, P.dres, n);
         // envlight.get_mip + trilinear mip blend; d/d rough through the level
         float lvl, dlvl;
         {
@@ -632,11 +683,11 @@ __global__ void __launch_bounds__(128) shade_splitsum_kernel(SsParams P) {
             float lin = alb[c] * dlv[c] + sa[c] * slv[c];
             float g = (lin >= 0.f && lin <= 1.f) ? 1.f : 0.f;
             colv[c] = fminf(fmaxf(lin, 0.f), 1.f);
-            P.jac[9 * pix + 3 * c + 0] = g * (dlv[c] + met * fg0 * slv[c]);
-            P.jac[9 * pix + 3 * c + 1] = g * ((alb[c] - 0.04f) * fg0 * slv[c]);
-            P.jac[9 * pix + 3 * c + 2] = g * ((F0 * dfg0 + dfg1) * slv[c] + sa[c] * dslv[c]);
+            s_jac[9 * lp + 3 * c + 0] = g * (dlv[c] + met * fg0 * slv[c]);
+            s_jac[9 * lp + 3 * c + 1] = g * ((alb[c] - 0.04f) * fg0 * slv[c]);
+            s_jac[9 * lp + 3 * c + 2] = g * ((F0 * dfg0 + dfg1) * slv[c] + sa[c] * dslv[c]);
+            s_col[3 * lp + c] = colv[c];
         }
-        st3(P.color, pix, mk3(colv[0], colv[1], colv[2]));
         if (P.albedo) st3(P.albedo, pix, mk3(alb[0], alb[1], alb[2]));
         if (P.roughness) P.roughness[pix] = rough;
         if (P.metalness) P.metalness[pix] = met;
@@ -644,6 +695,10 @@ __global__ void __launch_bounds__(128) shade_splitsum_kernel(SsParams P) {
         if (P.diff_light) st3(P.diff_light, pix, mk3(lin2srgb_f(dl.x), lin2srgb_f(dl.y), lin2srgb_f(dl.z)));
         if (P.spec_color) st3(P.spec_color, pix, mk3(lin2srgb_f(sa[0]), lin2srgb_f(sa[1]), lin2srgb_f(sa[2])));
         if (P.diff_color) st3(P.diff_color, pix, mk3(lin2srgb_f(alb[0]), lin2srgb_f(alb[1]), lin2srgb_f(alb[2])));
+        }
+        __syncthreads();
+        ss_stage_out(P.color, s_col, row0, rows, 3, threadIdx.x);
+        ss_stage_out(P.jac, s_jac, row0, rows, 9, threadIdx.x);
     }
     reg_kd = warp_sum(reg_kd); reg_ks = warp_sum(reg_ks);
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_reg[0], reg_kd); atomicAdd(&s_reg[1], reg_ks); }
@@ -809,7 +864,13 @@ extern "C" int dm_shade_splitsum_fwd(const dm_material_cfg* cfg, const float* fg
     P.color = color; P.jac = jac; P.reg_sums = reg_sums; P.albedo = albedo; P.roughness = roughness;
     P.metalness = metalness; P.spec_light = spec_light; P.diff_light = diff_light; P.spec_color = spec_color;
     P.diff_color = diff_color;
-    shade_splitsum_kernel<<<(unsigned)dm_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(P);
+    // persistent CTAs: 8 per SM (128 threads, ~10 KB static + the staged diffuse cube), grid = a multiple of the SM count
+    const size_t cube_bytes = (size_t)6 * diff_res * diff_res * 3 * sizeof(float);
+    P.dcube_smem = cube_bytes <= 24 * 1024 ? 1 : 0;
+    const size_t smem = P.dcube_smem ? cube_bytes : 0;
+    const int64_t chunks = dm_ceil_div(n, SS_CHUNK);
+    const int64_t grid = chunks < (int64_t)DM_NUM_SMS * 6 ? chunks : (int64_t)DM_NUM_SMS * 6;
+    shade_splitsum_kernel<<<(unsigned)grid, SS_CHUNK, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
     return DM_OK;
 }

@@ -373,6 +373,20 @@ def pad_convert(x_f32, cpad, scale=1.0, shift=0.0, dtype=torch.float16):
     return y
 
 
+def cond_gather(depth, normal_u8, light_u8, view_ids_i32, env_ids_i32, cpad=64, dtype=torch.float16, out=None):
+    """Resident pre-rendered maps -> ControlNet condition [B,H,W,cpad] (N1).  depth [V,H,W,1] fp32, normal [V,H,W,3] u8,
+    light [V,E,H,W,18] u8 on the device; ids int32 device tensors [B]."""
+    V, Hh, W = depth.shape[0], depth.shape[1], depth.shape[2]
+    B = view_ids_i32.shape[0]
+    assert depth.is_contiguous() and normal_u8.is_contiguous() and light_u8.is_contiguous()
+    assert normal_u8.dtype == torch.uint8 and light_u8.dtype == torch.uint8 and view_ids_i32.dtype == torch.int32
+    if out is None:
+        out = torch.empty(B, Hh, W, cpad, device=depth.device, dtype=dtype)
+    check(lib().dm_cond_gather(_dt_code(dtype), ptr_any(depth), ptr_any(normal_u8), ptr_any(light_u8), light_u8.shape[1], Hh * W,
+                               ptr_any(view_ids_i32), ptr_any(env_ids_i32), B, cpad, ptr_any(out), stream_ptr()), "dm_cond_gather")
+    return out
+
+
 def unpad_convert(x, cout, scale=1.0):
     bf = _is_bf16(x)
     assert x.is_contiguous()

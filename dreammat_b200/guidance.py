@@ -118,8 +118,12 @@ class _SDSLoss(torch.autograd.Function):
 class _DenseGraphs:
     """Static buffers + three captured CUDA graphs for the dense section (shapes fixed by B, H, W)."""
 
-    def __init__(self, guid, B, H, W):
+    def __init__(self, guid, B, H, W, maps=None):
         self.guid, self.B = guid, B
+        # N1: condition maps resident on the device as uint8 (scene.FixViewMaps); gathered + de-quantised inside the graph
+        self.maps = maps if (maps is not None and tuple(maps.depths.shape[1:3]) == (H, W) and guid.weights_dtype != torch.float32) else None
+        self.vid = torch.zeros(B, device=guid.device, dtype=torch.int32)
+        self.eid = torch.zeros(B, device=guid.device, dtype=torch.int32)
         dev, dt = guid.device, guid.weights_dtype
         h, w = H // 8, W // 8
         Dm = guid.unet.cfg.cross_attention_dim
@@ -172,7 +176,10 @@ class _DenseGraphs:
         zt = D.add_noise(self.z, self.noise, self.sqrt_ac, self.sqrt_1mac, rep=3, cpad=64, dtype=g.weights_dtype)
         down = mid = None
         if g.use_controlnet and scale != 0:
-            cond = D.pad_convert(self.cond, 64, 1.0, 0.0, g.weights_dtype)
+            if self.maps is not None:
+                cond = D.cond_gather(self.maps.depths, self.maps.normals, self.maps.lightmaps, self.vid, self.eid, 64, g.weights_dtype)
+            else:
+                cond = D.pad_convert(self.cond, 64, 1.0, 0.0, g.weights_dtype)
             down, mid = g.controlnet.forward(zt, self.t3, self.ctx, cond, scale)
         if self.fused_csd:
             R.fill_(self.sums, 0.0)
@@ -240,6 +247,7 @@ class StableDiffusionLightGuidance:
         # dreammat_guidance.py:92-94: fp16 weights unless half_precision_weights=false (then fp32 = the high-precision
         # mode of the kernels, csrc/dense_hp.cu); an explicit dtype (bf16: BASELINE config 3) overrides
         self.weights_dtype = dtype if dtype is not None else (torch.float16 if self.cfg.half_precision_weights else torch.float32)
+        self.maps = None              # optional device-resident scene.FixViewMaps (N1); set by the host / enable_graphs
         self.fuse_csd = True          # conv_out + CSD combination in one kernel where the shape allows (D.csd_supported)
         self.keep_debug = False       # parity tests: keep latents / eps / grad of the last evaluation in self.debug
         self.debug: Dict[str, torch.Tensor] = {}
@@ -333,13 +341,17 @@ class StableDiffusionLightGuidance:
         return out
 
     # ---- CUDA-graph path: the dense section has static shapes, so its ~900 launches are captured once
-    def enable_graphs(self, B: int, H: int, W: int):
+    def enable_graphs(self, B: int, H: int, W: int, maps=None):
         """Capture (1) VAE encode, (2) add_noise + ControlNet + UNet, (3) the VAE input-gradient as three CUDA graphs
-        over static buffers.  Schedules that change kernel arguments (the ControlNet scale) trigger a re-capture."""
-        self.graphs = _DenseGraphs(self, B, H, W)
+        over static buffers.  Schedules that change kernel arguments (the ControlNet scale) trigger a re-capture.
+        maps: a device-resident scene.FixViewMaps at the VAE input size -> the condition is gathered from it by (view, env) id."""
+        if maps is not None:
+            self.maps = maps
+        self.graphs = _DenseGraphs(self, B, H, W, maps)
         return self.graphs
 
-    def graph_step(self, cond_bhwc, ctx3, grad_scale: float, t=None, noise=None, vae_eps=None, mark=None):
+    def graph_step(self, cond_bhwc, ctx3, grad_scale: float, t=None, noise=None, vae_eps=None, mark=None, view_id=None,
+                   env_id=None):
         """One guidance evaluation through the captured graphs.  `graphs.rgb` must hold the rendered batch.
         Returns (d loss / d rgb [B,H,W,3], sums[10]) with d loss_sds / d latents = grad / B * grad_scale."""
         g = self.graphs
@@ -363,7 +375,10 @@ class StableDiffusionLightGuidance:
         ac = self.alphas[t]
         g.sqrt_ac.copy_(ac.sqrt()); g.sqrt_1mac.copy_((1 - ac).sqrt()); g.t3.copy_(torch.cat([t] * 3).float())
         g.ctx.copy_(ctx3)
-        g.cond.copy_(self._cond_to_latent_grid(cond_bhwc, g.noise.shape[-2], g.noise.shape[-1]))
+        if g.maps is not None:
+            g.vid.copy_(view_id.to(torch.int32)); g.eid.copy_(env_id.to(torch.int32))       # a few integers per step
+        else:
+            g.cond.copy_(self._cond_to_latent_grid(cond_bhwc, g.noise.shape[-2], g.noise.shape[-1]))
         if g.fused_csd:
             # the CSD combination, nan_to_num, d loss / d latents and the logged norms come out of conv_out's epilogue
             g.w1mac.copy_(1 - ac)

@@ -255,6 +255,22 @@ class FixViewMaps:
         self.depths, self.normals, self.lightmaps = (t.to(device) for t in (self.depths, self.normals, self.lightmaps))
         return self
 
+    @classmethod
+    def synthetic(cls, n_views: int, n_envs: int, height: int, width: int, device="cpu", seed: int = 0):
+        """Stand-in for the Blender pre-renders where they do not exist (benchmarks): same tensors, dtypes and value
+        ranges -- depth fp32 in {0} U [0.3, 1], normal / light uint8 -- generated on `device`."""
+        self = cls.__new__(cls)
+        g = torch.Generator(device=device).manual_seed(seed)
+        d = torch.rand(n_views, height, width, 1, device=device, generator=g)
+        self.depths = torch.where(d > 0.35, 0.3 + 0.7 * d, torch.zeros_like(d)).contiguous()
+        self.normals = torch.randint(0, 256, (n_views, height, width, 3), device=device, generator=g, dtype=torch.uint8)
+        self.lightmaps = torch.randint(0, 256, (n_views, n_envs, height, width, 18), device=device, generator=g, dtype=torch.uint8)
+        return self
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.depths, self.normals, self.lightmaps))
+
     def condition_map(self, view_id: torch.Tensor, env_id: torch.Tensor) -> torch.Tensor:
         """[B, H, W, 22] fp32 on the maps' device; channel order of uncond.py:581-582, :802."""
         v, e = view_id.to(self.depths.device), env_id.to(self.depths.device)

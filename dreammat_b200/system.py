@@ -190,7 +190,7 @@ class DreamMatMaterial:
         use_raytracing: bool = True
 
     def __init__(self, cfg: Optional[dict] = None, device="cuda", env_maps: Optional[List[torch.Tensor]] = None,
-                 fg_lut: Optional[torch.Tensor] = None, envlight: Optional[list] = None):
+                 fg_lut: Optional[torch.Tensor] = None, envlight: Optional[list] = None, envlight_cache_dir: Optional[str] = None):
         self.cfg = self.Config(**(cfg or {}))
         self.device = torch.device(device)
         c = self.cfg
@@ -208,8 +208,18 @@ class DreamMatMaterial:
                                   c.diffuse_sample_num, c.specular_sample_num)
         self.ss_cfg = MaterialCfg(c.min_metallic, c.max_metallic, c.min_roughness, c.max_roughness,
                                   c.diffuse_sample_num, c.specular_sample_num)
-        self.FG_LUT = fg_lut.to(self.device).contiguous() if fg_lut is not None else None
+        self.FG_LUT = fg_lut.to(self.device).reshape(fg_lut.shape[-3], fg_lut.shape[-2], 2).contiguous() if fg_lut is not None else None
         self.envlight = envlight  # [(diffuse_cube, [spec mips])] per env (split-sum branch)
+        if not c.use_raytracing:
+            # split-sum branch (dreammat_material.py:679-711,747-762): needs the FG LUT (:405-410) and one prefiltered
+            # EnvLight per map (:383, scale = environment_scale) -- built on the device, cached on disk (envlight.py)
+            if self.FG_LUT is None:
+                raise ValueError("use_raytracing=false needs the FG LUT (load/lights/bsdf_256_256.bin, scene.load_fg_lut)")
+            if self.envlight is None:
+                from .envlight import build_envlight
+                self.envlight = [build_envlight(m.to(self.device), scale=c.environment_scale, cache_dir=envlight_cache_dir)
+                                 for m in (env_maps or [])]
+            self._mip_ptrs = [(C.c_void_p * len(mips))(*[m.data_ptr() for m in mips]) for (_, mips) in self.envlight]
         self.bvh = None
 
     def export(self, features: torch.Tensor, **kwargs) -> Dict[str, Any]:
@@ -442,8 +452,13 @@ class DreamMat:
         # ---- who shades what.  Default: this rank's own views.  With the global batch known (`global_view_id` /
         # `global_env_id`, every view in the G-buffer cache) the covered pixels of ALL views are cut into equal intervals
         # (parallel.pixel_partition) so the ray-tracing load does not depend on which views a rank drew.
-        balanced = (self.world_size > 1 and self.balance_pixels and rng is None and "global_view_id" in batch and
+        balanced = (self.world_size > 1 and self.balance_pixels and "global_view_id" in batch and
                     self._balance_ok)      # rank-invariant: fixed by prepare_balanced(), never by local cache state
+        # explicit randomness (parity tests / bench --check): per-view lists indexed by the LOCAL view, or -- with
+        # rng["indexed_by"] == "global_view" -- by the view's position in the global batch (needed when pixels are balanced)
+        rng_global = rng is not None and rng.get("indexed_by") == "global_view"
+        if rng is not None and balanced and not rng_global:
+            raise ValueError("explicit randomness with pixel-balanced shading must be indexed by global view")
         if balanced:
             from .parallel import exchange_rows, pixel_partition
             gvid = [int(v) for v in batch["global_view_id"]]
@@ -459,7 +474,7 @@ class DreamMat:
             send_counts = counts[self.rank]
             recv_counts = [counts[r][self.rank] for r in range(self.world_size)]
         else:
-            my_segs = [(g, int(batch["env_id"][b]), 0, g["pn"], b) for b, g in enumerate(gbs)]
+            my_segs = [(g, int(batch["env_id"][b]), 0, g["pn"], (self.rank * B + b) if rng_global else b) for b, g in enumerate(gbs)]
         n_sh = sum(bb - a for (_, _, a, bb, _) in my_segs)
         self._last_pn = n_sh
         g_ = getattr(guid, "graphs", None)
@@ -482,7 +497,7 @@ class DreamMat:
             n = bb - a
             pts, nrm, vd = ge["pts"][a:bb], ge["nrm"][a:bb], ge["vd"][a:bb]
             if rng is not None:   # explicit randomness for parity tests
-                ang, eps, rd, rs = (rng[k][gi].to(dev).reshape(-1).contiguous() for k in ("rand_ang", "normal_eps", "rand_d", "rand_s"))
+                ang, eps, rd, rs = (rng[k][gi].to(dev).reshape(-1)[a:bb].contiguous() for k in ("rand_ang", "normal_eps", "rand_d", "rand_s"))
             else:
                 ang, eps = torch.rand(n, device=dev), torch.randn(n, device=dev) * ren.change_eps
                 rd, rs = torch.rand(n, device=dev), torch.rand(n, device=dev)
@@ -490,12 +505,18 @@ class DreamMat:
             f = torch.empty(n, 5, device=dev); fj = torch.empty(n, 5, device=dev)
             check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(pts), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(f), st), "hashgrid fwd")
             check(lib().dm_hashgrid_mlp_fwd(C.byref(geo.hg), ptr(pj), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(fj), st), "hashgrid fwd")
-            env = mat.light[env_id]
             color, jac = color_sh[o:o + n], jac_sh[o:o + n]
-            check(lib().dm_shade_mc_fwd(C.byref(mat.mc_cfg), ren.ray_tracer.h, ptr(env), env.shape[0], env.shape[1],
-                                        ptr(mat.tab_d), ptr(mat.tab_s), ptr(pts), ptr(nrm), ptr(vd), ptr(f),
-                                        ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
-                                        None, ptr(mat.perm), st), "dm_shade_mc_fwd")
+            if mat.cfg.use_raytracing:
+                env = mat.light[env_id]
+                check(lib().dm_shade_mc_fwd(C.byref(mat.mc_cfg), ren.ray_tracer.h, ptr(env), env.shape[0], env.shape[1],
+                                            ptr(mat.tab_d), ptr(mat.tab_s), ptr(pts), ptr(nrm), ptr(vd), ptr(f),
+                                            ptr(fj), ptr(rd), ptr(rs), n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7),
+                                            None, ptr(mat.perm), st), "dm_shade_mc_fwd")
+            else:   # use_raytracing=false: split-sum shading (dreammat_material.py:679-711), three texture lookups per pixel
+                dcube, mips = mat.envlight[env_id]
+                check(lib().dm_shade_splitsum_fwd(C.byref(mat.ss_cfg), ptr(mat.FG_LUT), mat.FG_LUT.shape[0], ptr(dcube), dcube.shape[1],
+                                                  mat._mip_ptrs[env_id], len(mips), mips[0].shape[1], ptr(nrm), ptr(vd), ptr(f), ptr(fj),
+                                                  n, ptr(color), ptr(jac), ptr(reg_sums), *([None] * 7), st), "dm_shade_splitsum_fwd")
             saved.append((pts, pj, f, fj, jac, n, o))
             o += n
         # colours travel to the ranks that own the views (one all-to-all); without balancing they are already home
@@ -519,17 +540,22 @@ class DreamMat:
                                                      guid.cfg.view_dependent_prompting, return_null_text_embeddings=True)
         if use_graphs:
             # dense section replayed from three captured CUDA graphs (VAE fwd | ControlNet+UNet | VAE bwd)
-            drgb, sums = guid.graph_step(batch["condition_map"], ctx3, lam_sds * B / Bg, mark=self._mark)
+            drgb, sums = guid.graph_step(batch.get("condition_map"), ctx3, lam_sds * B / Bg, mark=self._mark,
+                                         view_id=batch["view_id"], env_id=batch["env_id"])
             loss_sds = sums[0] / Bg
             dvae = drgb
         else:
             # guidance (dreammat_guidance.py:536-602): VAE encode with grad, ControlNet + UNet x3 under no_grad, CSD gradient
             from .guidance import _SDSLoss
             vae_in = vae_in.detach().requires_grad_(True)
-            lat = guid.encode_images(vae_in, rng["vae_eps"].to(dev) if rng is not None else None)
+            rsl = slice(self.rank * B, (self.rank + 1) * B) if rng_global else slice(None)
+            cond_map = batch.get("condition_map")
+            if cond_map is None:      # N1: the maps are a device-resident uint8 dataset; eager path gathers the float view of it
+                cond_map = guid.maps.condition_map(batch["view_id"], batch["env_id"])
+            lat = guid.encode_images(vae_in, rng["vae_eps"][rsl].to(dev) if rng is not None else None)
             self._mark("vae_fwd")
-            grad, dlat, sums = guid.compute_grad_sds(lat, batch["condition_map"], ctx3, rng["t"].to(dev) if rng is not None else None,
-                                                     rng["noise"].to(dev) if rng is not None else None)
+            grad, dlat, sums = guid.compute_grad_sds(lat, cond_map, ctx3, rng["t"][rsl].to(dev) if rng is not None else None,
+                                                     rng["noise"][rsl].to(dev) if rng is not None else None)
             self._mark("unet_cn")
             loss_sds = _SDSLoss.apply(lat, dlat, sums[0] / B) * (B / Bg)          # mean over the GLOBAL batch of views
             (lam_sds * loss_sds).backward()
@@ -558,7 +584,7 @@ class DreamMat:
         dcolor_sh = exchange_rows(dcolor_own[:own_px], recv_counts, send_counts, self.world_size) if balanced else dcolor_own
         for (pts, pj, f, fj, jac, n, o) in saved:
             df = torch.empty(n, 5, device=dev); dfj = torch.empty(n, 5, device=dev)
-            check(lib().dm_shade_bwd(C.byref(mat.mc_cfg), ptr(f), ptr(fj), ptr(dcolor_sh[o:o + n]), ptr(jac), lam_reg * 0.25 / total_pn,
+            check(lib().dm_shade_bwd(C.byref(mat.mc_cfg if mat.cfg.use_raytracing else mat.ss_cfg), ptr(f), ptr(fj), ptr(dcolor_sh[o:o + n]), ptr(jac), lam_reg * 0.25 / total_pn,
                                      lam_reg * 0.1 / total_pn, n, ptr(df), ptr(dfj), st), "dm_shade_bwd")
             for pts_, d_ in ((pts, df), (pj, dfj)):
                 check(lib().dm_hashgrid_mlp_bwd(C.byref(geo.hg), ptr(pts_), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(d_),

@@ -189,6 +189,15 @@ int dm_sds_grad(const float* eps_pred, const float* noise, const float* w, int B
                 float c_uncond, float c_null, float c_noise, float* grad, float* dlatents, float* norms,
                 void* stream);
 
+/* ------------------------------------------------------------------ split-sum environment lights (a5 / N4)
+ * Device-side build of `envlight.EnvLight(path, scale)` (ashawkey/envlight wrapping nvdiffrec renderutils, un-vendored;
+ * models/materials/dreammat_material.py:379-386): lat-long HDR [H,W,3] * scale -> cube [6,res,res,3]; 2x2-average mips;
+ * mode 0 cosine (diffuse) / mode 1 GGX-prefiltered (specular, alpha^2 = roughness^4, texels with N.L >= cos_cutoff)
+ * convolution at equal resolution.  Host driver + disk cache: dreammat_b200/envlight.py. */
+int dm_envlight_latlong_to_cube(const float* latlong, int H, int W, float scale, int res, float* cube, void* stream);
+int dm_envlight_downsample(const float* cube, int res, float* out, void* stream);
+int dm_envlight_filter(const float* cube, int res, int mode, float roughness, float cos_cutoff, float* out, void* stream);
+
 /* ------------------------------------------------------------------ dense path (a7, a8)
  * Tensor-core (tcgen05 + TMA + TMEM) contraction used for every conv / linear of the VAE encoder,
  * UNet and ControlNet: replaces the cuDNN / cuBLAS kernels diffusers dispatches from
@@ -282,6 +291,11 @@ int dm_softmax_bwd(int bf16, const void* P, const void* dP, int64_t rows, int co
 /* fp32 [rows,cin] -> T [rows,cpad] (x*scale+shift, zero padding) and back (first cout channels, * scale) */
 int dm_pad_convert(int bf16, const float* x, int64_t rows, int cin, int cpad, float scale, float shift, void* y,
                    void* stream);
+/* N1: gather + de-quantise the resident pre-rendered condition maps (data/uncond.py:532-582,799-802) straight into the
+ * channel-padded ControlNet condition [B, HW, cpad] (storage dtype): depth fp32 [V,HW] | normal u8 [V,HW,3] / 255 |
+ * light u8 [V,E,HW,18] / 255 for the batch's (view_ids[b], env_ids[b]); the fp32 condition_map never exists. */
+int dm_cond_gather(int bf16, const float* depth, const uint8_t* normal, const uint8_t* light, int n_env, int64_t HW,
+                   const int32_t* view_ids, const int32_t* env_ids, int B, int cpad, void* out, void* stream);
 int dm_unpad_convert(int bf16, const void* x, int64_t rows, int ld, int cout, float scale, float* y, void* stream);
 int dm_nhwc_to_nchw_f32(int bf16, const void* x, int n, int HW, int ld, int C, float* y, void* stream);
 /* DiagonalGaussianDistribution.sample() * scaling_factor (dreammat_guidance.py:290-291) and its backward */

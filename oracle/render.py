@@ -245,8 +245,8 @@ def shade_raytracing(pts, normals, view_dirs, light, metallic, roughness, albedo
     sample_specular_directions :575-596, get_lights :490-507 (is_train=True, random_azimuth=True).
 
     rand_d / rand_s: [pn,1,1] uniform draws (appendix B #5/#6).  trace_fn(o,d)->hit mask."""
-    tab_d = direction_tables(n_diffuse)
-    tab_s = direction_tables(n_specular)
+    tab_d = direction_tables(n_diffuse).to(pts.device)      # device-generic: bench.py's stock-PyTorch-CUDA leg runs this on the GPU
+    tab_s = direction_tables(n_specular).to(pts.device)
     reflections = torch.sum(view_dirs * normals, -1, keepdim=True) * normals * 2 - view_dirs
     F0 = 0.04 * (1 - metallic) + metallic * albedo
 
@@ -306,7 +306,7 @@ def shade_raytracing(pts, normals, view_dirs, light, metallic, roughness, albedo
     pts_ = pts.unsqueeze(1).repeat(1, sn, 1)
     o = pts_.reshape(-1, 3) + directions.reshape(-1, 3).detach() * 1e-5
     hit = trace_fn(o, directions.reshape(-1, 3).detach()).reshape(-1, sn)
-    lights = torch.zeros(pts.shape[0], sn, 3, dtype=light.dtype)
+    lights = torch.zeros(pts.shape[0], sn, 3, dtype=light.dtype, device=pts.device)
     miss = ~hit
     if miss.any():
         lights[miss] = envmap_lookup(light, directions.detach()[miss])

@@ -1,6 +1,7 @@
 """Run the dominant kernels once each at north-star sizes (for `ncu --set full -k regex:...`)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.chdir(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dreammat_b200 import dense_ops as D, render_ops as R
 from dreammat_b200._cabi import MaterialCfg
@@ -26,6 +27,12 @@ if which in ("all", "shade"):
         ff = R.hashgrid_mlp(g["pts"], geo.grid.detach().requires_grad_(True), geo.W1, geo.W2, geo.hg)
         ff.sum().backward()
     torch.cuda.synchronize()
+if which in ("splitsum",):
+    import bench
+    sysm, cams = bench.build_system(dev, 512, 100000, (256, 512), 0, torch.float16, "splitsum")
+    c = cams.cameras(torch.tensor([3]))
+    g = sysm.renderer.gbuffer(c["rays_o"].to(dev), c["rays_d"].to(dev), c["mvp_mtx"].to(dev), c["w2c"].to(dev), 3)
+    print("splitsum", bench.splitsum_kernel_roofline(sysm, 6483.9))
 if which in ("all", "dense"):
     x = torch.randn(8, 512, 512, 128, device=dev).half(); w = (torch.randn(128, 9 * 128, device=dev) * 0.03).half()
     gm = torch.ones(128, device=dev).half(); bt = torch.zeros(128, device=dev).half()

@@ -235,6 +235,21 @@ def test_guidance_step_matches_oracle(small):
     assert e_g < max(2 * floor, TOL16) and e_r < max(3 * floor, 3 * TOL16)
 
 
+def test_cond_gather_bit_exact_vs_float_condition_map():
+    """N1: gathering + de-quantising the resident uint8 maps inside the kernel gives the SAME fp16 condition tensor as the
+    reference's float condition_map (uncond.py:799-802) followed by the channel-padding cast."""
+    from dreammat_b200 import dense_ops as D
+    from dreammat_b200.scene import FixViewMaps
+    maps = FixViewMaps.synthetic(6, 3, 64, 64, device="cuda", seed=3)
+    v, e = torch.tensor([4, 0, 5, 4]), torch.tensor([2, 1, 0, 0])
+    ref = D.pad_convert(maps.condition_map(v, e), 64, 1.0, 0.0, torch.float16)
+    got = D.cond_gather(maps.depths, maps.normals, maps.lightmaps, v.int().cuda(), e.int().cuda(), 64, torch.float16)
+    assert got.shape == (4, 64, 64, 64) and torch.equal(got, ref)
+    assert float(got[..., 22:].abs().max()) == 0.0 and float(got[..., :22].float().abs().sum()) > 0
+    refb = D.pad_convert(maps.condition_map(v, e), 64, 1.0, 0.0, torch.bfloat16)
+    assert torch.equal(D.cond_gather(maps.depths, maps.normals, maps.lightmaps, v.int().cuda(), e.int().cuda(), 64, torch.bfloat16), refb)
+
+
 def test_fused_csd_epilogue_matches_unfused(small):
     """J1: conv_out with the CSD combination fused into its epilogue (dm_conv2d_csd).
     (1) op level, same input activation: the noise predictions it emits equal conv_out + layout change (D.conv2d +
