@@ -350,7 +350,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-MC_THREAD_INSTR_PER_RAY = 2100     # measured: ncu thread-level instructions of shade_mc_kernel / rays (profiles/r02_shade_frontier.md)
+MC_THREAD_INSTR_PER_RAY = 2290     # measured: ncu thread-level instructions of shade_mc_kernel / rays (profiles/r02_shade_frontier.md)
 
 
 def splitsum_kernel_roofline(sysm, hbm):

@@ -109,6 +109,7 @@ struct McParams {
     uint32_t* hit_bits;
     int skip_horizon;   // dm_tune knob
     int frontier;       // dm_tune "mc_frontier": shared-origin traversal (see origin_frontier below)
+    int defer;          // dm_tune "mc_defer": rays that need the divergent descent are compacted first (phase B of the sample loop)
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
@@ -281,6 +282,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
     float* s_td = s_tab;
     float* s_ts = s_tab + 3 * nd;
     uint16_t* s_list = reinterpret_cast<uint16_t*>(s_tab + 3 * nd + 2 * ns);   // [MC_WARPS][S] compacted sample ids
+    // deferred-ray work list: [MC_WARPS][S] box masks (8-byte aligned) then [MC_WARPS][S] sample ids
+    unsigned long long* s_wl_mask = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(s_list + MC_WARPS * S) + 7u) & ~static_cast<uintptr_t>(7));
+    unsigned short* s_wl_id = reinterpret_cast<unsigned short*>(s_wl_mask + (size_t)MC_WARPS * S);
     for (int i = threadIdx.x; i < nd; i += blockDim.x) {
         float ua = P.tab_d[2 * i], ue = P.tab_d[2 * i + 1];
         s_td[3 * i] = ua * PI_F * 2.0f;            // az = az * pi * 2 (:563)
@@ -361,16 +366,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
             count = S;
         }
         __syncwarp();
-        // ---- sample loop (lane = slot of the work list).  Samples are visited in table order: Fibonacci points sorted by
-        // elevation, so the 32 rays of a pass leave the surface at the same angle and have similar traversal lengths
-        // (direction-coherent orders measured 10 % slower, profiles/r01_shade_experiments.md).
-        for (int base = 0; base < count; base += 32) {
-            if (base + lane >= count) continue;
-            const int s = list[base + lane];
-            const bool spec = s >= nd;
-            // ---- sample direction (value and d/da), :554-596
+        // ---- per-sample pieces shared by the two phases below
+        auto sample_dir = [&](int s) -> D3 {                       // sample direction (value and d/da), :554-596
             D3 d;
-            if (!spec) {
+            if (s < nd) {
                 float az = s_td[3 * s] + px.rd;
                 az = az - floorf(az / TWO_PI_F) * TWO_PI_F;  // % (2 pi)
                 float sn, cs;
@@ -383,47 +382,11 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
                 const int j = s - nd;
                 d = spec_direction(px, s_ts[2 * j], s_ts[2 * j + 1]);
             }
+            return d;
+        };
+        auto shade_sample = [&](int s, const D3& d) {             // unoccluded sample: BRDF terms (value and d/da) + env texel (:615-677)
+            const bool spec = s >= nd;
             const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
-            // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless the
-            // aux light maps are requested its radiance is never used, so the ray need not be traced
-            if (P.skip_horizon && spec && !P.spec_light && !P.hit_bits &&
-                (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f) continue;
-            // ---- occlusion first (:490-507): occluded samples contribute nothing, skip their BRDF math
-            bool hit = false;
-            {
-                f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
-                if (use_frontier) {
-                    // (1) the triangles around p: warp-uniform loop, broadcast loads
-                    for (int li = 0; li < FR.nl; ++li) {
-                        const int code = ~FR.leaf[li];
-                        const int first = code >> 2, cnt = (code & 3) + 1;
-                        for (int k = 0; k < cnt; ++k) {
-                            const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
-                            const float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
-                            float u, v;
-                            if (!hit && tri_hit_pre(o, dv, A, B, C, u, v) < DM_RT_MAX_DIST) hit = true;
-                        }
-                    }
-                    if (!hit) {
-                        // (2) frontier boxes: warp-uniform loop over shared memory; (3) divergent descent into the hit ones
-                        const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
-                        const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-                        unsigned long long mask = 0ull;
-                        for (int i = 0; i < FR.nf; ++i) {
-                            float tn;
-                            if (slab2(FR.box[i][0], FR.box[i][1], FR.box[i][2], FR.box[i][3], FR.box[i][4], FR.box[i][5], inv, oi,
-                                      DM_RT_MAX_DIST, tn)) mask |= 1ull << i;
-                        }
-                        hit = anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi);
-                    }
-                } else {
-                    float bt, bu, bvv; int bid;
-                    hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
-                }
-            }
-            if (P.hit_bits && hit) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
-            if (hit) continue;
-            // ---- unoccluded sample: BRDF terms (value and d/da) and the env texel (:615-677)
             const f3 n = mk3(px.n[0], px.n[1], px.n[2]), v = mk3(px.v[0], px.v[1], px.v[2]);
             const Dual aD = mkd(px.a, 1.0f);
             D3 h; h.x = d.x + v.x; h.y = d.y + v.y; h.z = d.z + v.z;   // H = normalize(v + d) (:513-514)
@@ -451,6 +414,89 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
                 float lwd = L[c] * w.d;
                 Ud[c] += lwd; Vd[c] += lwd * fh.v;
                 Wd[c] += lw * fh.d;
+            }
+        };
+        auto mark_hit = [&](int s) {
+            if (P.hit_bits) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
+        };
+        const bool horizon_cull = P.skip_horizon && !P.spec_light && !P.hit_bits;
+        // ---- phase A (lane = slot of the work list, all lanes in step).  Samples are visited in table order (Fibonacci points
+        // sorted by elevation).  With the frontier: local triangles and frontier boxes are tested here, coherently; a ray
+        // that is neither occluded by a local triangle nor clear of every frontier box is DEFERRED: (sample id, box mask)
+        // goes to a per-warp list in shared memory (ballot-compacted), so that phase B descends with every lane holding a
+        // ray that really needs the divergent traversal (the undeferred version ran that part at 5 of 32 lanes).
+        unsigned short* wl_id = s_wl_id + warp * S;
+        unsigned long long* wl_mask = s_wl_mask + (size_t)warp * S;
+        int wl_count = 0;
+        const bool defer = use_frontier && P.defer;
+        for (int base = 0; base < count; base += 32) {
+            const bool in_range = base + lane < count;
+            const int s = in_range ? list[base + lane] : 0;
+            const D3 d = sample_dir(s);
+            const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+            // a specular sample below the horizon has NoL = 0 -> G = 0 -> weight and d(weight)/da exactly 0: unless the
+            // aux light maps are requested its radiance is never used, so the ray need not be traced
+            const bool valid = in_range && !(horizon_cull && s >= nd && (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f);
+            // ---- occlusion first (:490-507): occluded samples contribute nothing, skip their BRDF math
+            bool hit = false, need = false;
+            unsigned long long mask = 0ull;
+            const f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
+            if (use_frontier) {
+                // (1) the triangles around p: warp-uniform loop, broadcast loads
+                for (int li = 0; li < FR.nl; ++li) {
+                    const int code = ~FR.leaf[li];
+                    const int first = code >> 2, cnt = (code & 3) + 1;
+                    for (int k = 0; k < cnt; ++k) {
+                        const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
+                        const float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+                        float u, v;
+                        if (valid && !hit && tri_hit_pre(o, dv, A, B, C, u, v) < DM_RT_MAX_DIST) hit = true;
+                    }
+                }
+                // (2) frontier boxes: warp-uniform loop over shared memory
+                const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
+                const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+                if (valid && !hit) {
+                    for (int i = 0; i < FR.nf; ++i) {
+                        float tn;
+                        if (slab2(FR.box[i][0], FR.box[i][1], FR.box[i][2], FR.box[i][3], FR.box[i][4], FR.box[i][5], inv, oi,
+                                  DM_RT_MAX_DIST, tn)) mask |= 1ull << i;
+                    }
+                    need = mask != 0ull;
+                }
+                if (!defer && need) {         // (3) undeferred: divergent descent right here
+                    hit = anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi);
+                    need = false;
+                }
+            } else if (valid) {
+                float bt, bu, bvv; int bid;
+                hit = bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv);
+            }
+            if (defer) {
+                const unsigned bal = __ballot_sync(0xffffffffu, need);
+                if (need) {
+                    const int pos = wl_count + __popc(bal & ((1u << lane) - 1u));
+                    wl_id[pos] = (unsigned short)s; wl_mask[pos] = mask;
+                }
+                wl_count += __popc(bal);
+            }
+            if (valid && hit) mark_hit(s);
+            if (valid && !hit && !need) shade_sample(s, d);
+        }
+        // ---- phase B: the deferred rays, 32 at a time, every lane with a live ray at entry
+        if (defer) {
+            __syncwarp();
+            for (int base = 0; base < wl_count; base += 32) {
+                if (base + lane >= wl_count) continue;
+                const int s = wl_id[base + lane];
+                const unsigned long long mask = wl_mask[base + lane];
+                const D3 d = sample_dir(s);
+                const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+                const f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
+                const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
+                const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+                if (anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi)) mark_hit(s);
+                else shade_sample(s, d);
             }
         }
 #pragma unroll
@@ -761,6 +807,7 @@ static int g_mc_frontier = 1;     // dm_tune "mc_frontier": 0 root traversal | 1
 static int g_mc_persistent = 0;   // dm_tune "mc_persistent": 1 = persistent warps with a static pixel interleave (measured slower:
                                   // per-pixel cost varies ~1:5, the hardware's CTA scheduler balances better), 0 = one CTA per MC_WARPS pixels
 static int g_mc_warps = 8;        // dm_tune "mc_warps": pixels (warps) per CTA, 1 | 2 | 4 | 8
+static int g_mc_defer = 1;        // dm_tune "mc_defer": 1 = compact the rays that need the divergent descent before descending
 extern int g_bvh_leaf_max;
 
 /* experiment knobs of the MC shader's traversal scheduling (not part of the reference surface) */
@@ -769,6 +816,7 @@ extern "C" int dm_tune(const char* key, int value) {
     if (!strcmp(key, "mc_skip_horizon")) g_mc_skip_horizon = value;
     else if (!strcmp(key, "mc_frontier")) g_mc_frontier = value;
     else if (!strcmp(key, "mc_persistent")) g_mc_persistent = value;
+    else if (!strcmp(key, "mc_defer")) g_mc_defer = value;
     else if (!strcmp(key, "mc_warps")) {
         if (value != 1 && value != 2 && value != 4 && value != 8) { dm_set_error("dm_tune mc_warps: 1, 2, 4 or 8"); return DM_EINVAL; }
         g_mc_warps = value;
@@ -802,6 +850,7 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.diff_light = diff_light; P.spec_color = spec_color; P.diff_color = diff_color; P.hit_bits = hit_bits; P.perm = sample_perm;
     P.skip_horizon = g_mc_skip_horizon;
     P.frontier = g_mc_frontier;
+    P.defer = g_mc_defer;
     return launch_mc(P, (cudaStream_t)stream);
 }
 
@@ -809,8 +858,9 @@ namespace {
 template <int W>
 int launch_mc_w(const McParams& P, cudaStream_t st) {
     // direction tables + one compacted sample-id list per warp
-    const size_t smem = (size_t)(3 * P.cfg.n_diffuse + 2 * P.cfg.n_specular) * sizeof(float) +
-                        (size_t)W * (P.cfg.n_diffuse + P.cfg.n_specular) * sizeof(uint16_t);
+    const size_t S_ = (size_t)(P.cfg.n_diffuse + P.cfg.n_specular);
+    const size_t smem = (size_t)(3 * P.cfg.n_diffuse + 2 * P.cfg.n_specular) * sizeof(float) + (size_t)W * S_ * sizeof(uint16_t) + 8 +
+                        (size_t)W * S_ * (sizeof(unsigned long long) + sizeof(unsigned short));
     static size_t smem_configured = 0;
     if (smem > smem_configured) {
         DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -87,28 +87,36 @@ def test_fused_step_matches_oracle():
     g_dev = geo.grads.detach().cpu().clone()
     p1 = geo.params.detach().cpu().clone()
 
-    # ---------------- oracle
+    # ---------------- oracle (q = the storage-rounding hook: fp16 emulation like the product, or identity = pure fp32)
     meta, _ = OR.hashgrid_meta()
-    P = p0.clone().requires_grad_(True)
-    grid, W1, W2 = P[:geo.n_grid], P[geo.n_grid:geo.n_grid + geo.n_w1].view(64, 32), P[geo.n_grid + geo.n_w1:].view(5, 64)
-    canv, ms, mjs = [], [], []
-    for b, v in enumerate(views):
-        f = OR.geometry_forward(v["pts"], grid, W1, W2, meta)
-        fj = OR.geometry_forward(OR.jitter_positions(v["pts"], v["nrm"], v["rand_ang"], v["normal_eps"]), grid, W1, W2, meta)
-        al, me, ro, _ = OR.material_params(f, fj)
-        ms.append(torch.sigmoid(f)); mjs.append(torch.sigmoid(fj))
-        o = OR.shade_raytracing(v["pts"], v["nrm"], v["vd"], envs[int(env_id[b])], me, ro, al, v["rand_d"], v["rand_s"],
-                                lambda oo, dd: sc["tracer"].trace(oo, dd)[1])
-        c = torch.ones(res * res, 3)
-        c = c.index_put((v["pix"].long(),), o["color"])
-        c = OR.antialias_apply(c, v["aa_oracle"])
-        canv.append(c.view(1, res, res, 3))
-    comp = torch.cat(canv, 0)
-    reg = OR.material_smoothness_grad(torch.cat(ms), torch.cat(mjs))
-    ctx3 = Q(pu.get_text_embeddings(el, az, dist, True, return_null_text_embeddings=True))
-    loss_sds, grad_o, _ = OS.guidance_step(wv, wc, wu, ucfg, vcfg, comp, cond, ctx3, t, noise, veps,
-                                           scales=(1.05, -0.7, -0.2, 0.0), cond_scale=1.0, q=Q)
-    (loss_sds + reg).backward()
+
+    def oracle_step(q):
+        P = p0.clone().requires_grad_(True)
+        grid, W1, W2 = P[:geo.n_grid], P[geo.n_grid:geo.n_grid + geo.n_w1].view(64, 32), P[geo.n_grid + geo.n_w1:].view(5, 64)
+        canv, ms, mjs = [], [], []
+        for b, v in enumerate(views):
+            f = OR.geometry_forward(v["pts"], grid, W1, W2, meta)
+            fj = OR.geometry_forward(OR.jitter_positions(v["pts"], v["nrm"], v["rand_ang"], v["normal_eps"]), grid, W1, W2, meta)
+            al, me, ro, _ = OR.material_params(f, fj)
+            ms.append(torch.sigmoid(f)); mjs.append(torch.sigmoid(fj))
+            o = OR.shade_raytracing(v["pts"], v["nrm"], v["vd"], envs[int(env_id[b])], me, ro, al, v["rand_d"], v["rand_s"],
+                                    lambda oo, dd: sc["tracer"].trace(oo, dd)[1])
+            c = torch.ones(res * res, 3)
+            c = c.index_put((v["pix"].long(),), o["color"])
+            c = OR.antialias_apply(c, v["aa_oracle"])
+            canv.append(c.view(1, res, res, 3))
+        comp = torch.cat(canv, 0)
+        reg = OR.material_smoothness_grad(torch.cat(ms), torch.cat(mjs))
+        ctx3 = q(pu.get_text_embeddings(el, az, dist, True, return_null_text_embeddings=True))
+        loss_sds, grad_o, _ = OS.guidance_step(wv, wc, wu, ucfg, vcfg, comp, cond, ctx3, t, noise, veps,
+                                               scales=(1.05, -0.7, -0.2, 0.0), cond_scale=1.0, q=q)
+        (loss_sds + reg).backward()
+        return P, comp, reg, loss_sds
+    P, comp, reg, loss_sds = oracle_step(Q)
+    P32, _, _, loss32 = oracle_step(OS.Ident)
+    # what fp16 storage itself costs on this chain, measured by the oracle: fp16-emulating vs pure fp32
+    floor_g = rel_err(P.grad, P32.grad)
+    floor_l = abs(float(loss_sds) - float(loss32)) / abs(float(loss32))
     opt = torch.optim.Adam([P], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
     opt.step()
     e_rgb = rel_err(out["comp_rgb"].cpu(), comp.detach())
@@ -116,15 +124,19 @@ def test_fused_step_matches_oracle():
     e_lr = abs(float(out["loss_mat_reg"]) - float(reg)) / abs(float(reg))
     e_g = rel_err(g_dev, P.grad)
     e_p = rel_err(p1 - p0, P.detach() - p0)
-    print(f"\nfused step small: rgb {e_rgb:.2e} loss_sds {e_ls:.2e} mat_reg {e_lr:.2e} param-grad {e_g:.2e} adam-update {e_p:.2e}")
-    assert e_rgb < 1e-3           # north_star: 1e-3 relative on rendered RGB (fp32 path)
-    assert e_ls < 2e-2 and e_lr < 1e-4
-    # the parameter gradient inherits the fp16 CSD noise floor (see test_gpu_dense.py); the fp32 part of the
-    # chain (shader + hash grid) is pinned to 1e-3 by test_gpu_render.py
-    assert e_g < 5e-2
-    # Adam's first step is sign-like (|update| = lr): compare where the oracle's gradient is not ~0
     big = P.grad.abs() > 1e-3 * P.grad.abs().max()
-    assert rel_err((p1 - p0)[big], (P.detach() - p0)[big]) < 5e-2
+    e_pb = rel_err((p1 - p0)[big], (P.detach() - p0)[big])
+    print(f"\nfused step small (fp16 mode): rgb {e_rgb:.2e} loss_sds {e_ls:.2e} (fp16 floor {floor_l:.2e}) mat_reg {e_lr:.2e} "
+          f"param-grad {e_g:.2e} (fp16 floor {floor_g:.2e}) adam-update {e_p:.2e}, {e_pb:.2e} where |g| > 1e-3 max")
+    assert e_rgb < 1e-3           # north_star: 1e-3 relative on rendered RGB (fp32 path)
+    assert e_lr < 1e-4 and e_ls < max(2 * floor_l, 1e-3)
+    # fp16 mode: the parameter gradient inherits the fp16 noise of the CSD combination (the three branches nearly cancel);
+    # the bound is 2x the floor the oracle itself measures between fp16 emulation and fp32.  The fp32 mode of the same
+    # step is held to 1e-3 in test_gpu_config1.py.
+    assert e_g < 2 * floor_g, (e_g, floor_g)
+    # Adam's first step with eps=1e-15 is sign-like (|update| = lr whatever |g|): a coordinate whose fp16-noisy gradient
+    # changes sign moves by 2 lr.  Compared where the oracle's gradient is not ~0; bound = the sign-flip rate fp16 noise allows
+    assert e_pb < max(4 * floor_g, 5e-2)
 
 
 def test_training_step_runs_through_autograd_wrappers():
