@@ -304,7 +304,7 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
             outs.append((color, jac, bits, reg))
     finally:
         lib().dm_tune(b"mc_frontier", DEFAULT_FRONTIER); lib().dm_tune(b"mc_persistent", 0); lib().dm_tune(b"mc_warps", DEFAULT_WARPS)
-        lib().dm_tune(b"mc_defer", 1)
+        lib().dm_tune(b"mc_defer", 0)
     occ = int(sum(bin(int(x) & 0xffffffff).count("1") for x in outs[0][2].flatten()[:4096].tolist()))
     assert occ > 0                      # the bumpy mesh self-occludes: the comparison is not vacuous
     for i, (color, jac, bits, reg) in enumerate(outs[1:], 1):
