@@ -34,5 +34,22 @@ def run():
     loss_o.backward()
     rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())  # noqa: E731
     e_z, e_g, e_r = rel(lat.detach(), z_o.detach()), rel(grad, grad_o), rel(x.grad, xo.grad)
-    print(f"smoke (dense): latents rel err {e_z:.2e}, sds-grad {e_g:.2e}, d-rgb {e_r:.2e} (fp16 path)")
-    assert e_z < 5e-3 and e_g < 5e-2 and e_r < 5e-2, (e_z, e_g, e_r)
+    # the fp16 floor of the same chain, measured by the oracle itself (fp16 emulation vs pure fp32)
+    w32 = (O.random_unet_weights(ucfg, 0), O.random_controlnet_weights(ucfg, 1), O.random_vae_weights(vcfg, 2))
+    x32 = rgb.clone().requires_grad_(True)
+    loss32, grad32, z32 = O.guidance_step(w32[2], w32[1], w32[0], ucfg, vcfg, x32, cond, ctx3, t, noise, veps, scales=(1.05, -0.7, -0.2, 0.0))
+    loss32.backward()
+    f_g, f_r = rel(grad_o, grad32), rel(xo.grad, x32.grad)
+    print(f"smoke (dense, fp16 mode): latents rel err {e_z:.2e}, sds-grad {e_g:.2e} (oracle fp16 floor {f_g:.2e}), d-rgb {e_r:.2e} (floor {f_r:.2e})")
+    assert e_z < 5e-3 and e_g < max(2 * f_g, 5e-3) and e_r < max(2 * f_r, 5e-3), (e_z, e_g, e_r, f_g, f_r)
+    # the same slice in the high-precision mode (half_precision_weights=false): north_star's 1e-3 on the SDS gradient
+    guid32 = StableDiffusionLightGuidance(dict(use_controlnet=True, control_types=["light"], condition_scales=[1.0], cond_scale=1.05,
+                                               uncond_scale=-0.7, null_scale=-0.2, half_precision_weights=False),
+                                          Wt.UNetConfig(**ucfg.__dict__), Wt.VAEConfig(**vcfg.__dict__), *w32, dev)
+    xh = rgb.to(dev).requires_grad_(True)
+    lat_h = guid32.encode_images(xh, veps.to(dev))
+    grad_h, dlat_h, sums_h = guid32.compute_grad_sds(lat_h, cond.to(dev), ctx3, t.to(dev), noise.to(dev))
+    _SDSLoss.apply(lat_h, dlat_h, sums_h[0] / B).backward()
+    h_z, h_g, h_r = rel(lat_h.detach(), z32.detach()), rel(grad_h, grad32), rel(xh.grad, x32.grad)
+    print(f"smoke (dense, fp32 mode on the bf16x3 tcgen05 path): latents {h_z:.2e}, sds-grad {h_g:.2e}, d-rgb {h_r:.2e} vs the pure fp32 oracle")
+    assert h_z < 1e-3 and h_g < 1e-3 and h_r < 1e-3, (h_z, h_g, h_r)
