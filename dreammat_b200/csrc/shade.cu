@@ -109,7 +109,8 @@ struct McParams {
     uint32_t* hit_bits;
     int skip_horizon;   // dm_tune knob
     int frontier;       // dm_tune "mc_frontier": shared-origin traversal (see origin_frontier below)
-    int defer;          // dm_tune "mc_defer": rays that need the divergent descent are compacted first (phase B of the sample loop)
+    int defer;          // dm_tune "mc_defer": 0 off | 1 every ray that needs a descent is compacted first (phase B of the sample loop)
+                        // | N > 1 rays whose descent exceeds N node steps are re-queued and finished together in phase B
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
 };
 
@@ -229,15 +230,17 @@ __device__ __forceinline__ void refine_frontier(const BvhView& bv, f3 p, Frontie
     __syncwarp();
 }
 
-// any-hit over the frontier subtrees selected by `mask` (bit i = F.code[i]); same node / leaf steps as bvh_trace<true>
-__device__ __forceinline__ bool anyhit_subtrees(const BvhView& bv, const FrontierList& F, unsigned long long mask, f3 o, f3 d,
-                                                f3 inv, f3 oi) {
+// any-hit over the frontier subtrees selected by `mask` (bit i = F.code[i]); same node / leaf steps as bvh_trace<true>.
+// Returns 0 = no hit, 1 = hit, 2 = `budget` node / leaf steps used up without a verdict (the caller re-queues the ray).
+__device__ __forceinline__ int anyhit_subtrees(const BvhView& bv, const FrontierList& F, unsigned long long mask, f3 o, f3 d,
+                                               f3 inv, f3 oi, int budget) {
     int stack[DM_BVH_STACK];
     int sp = 0, cur = 0;
     bool alive = mask != 0ull;
     if (alive) { const int i = __ffsll((long long)mask) - 1; mask &= mask - 1ull; cur = F.code[i]; }
     while (alive) {
         while (alive && cur >= 0) {
+            if (--budget < 0) return 2;
             const float4* n = bv.nodes + (int64_t)cur * 4;
             float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
             float tl, tr;
@@ -262,18 +265,20 @@ __device__ __forceinline__ bool anyhit_subtrees(const BvhView& bv, const Frontie
                 const float4* tp = bv.tris + (int64_t)(first + k) * 3;
                 float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
                 float u, v;
-                if (tri_hit_pre(o, d, A, B, C, u, v) < DM_RT_MAX_DIST) return true;
+                if (tri_hit_pre(o, d, A, B, C, u, v) < DM_RT_MAX_DIST) return 1;
             }
         }
         if (sp > 0) cur = stack[--sp];
         else if (mask) { const int i = __ffsll((long long)mask) - 1; mask &= mask - 1ull; cur = F.code[i]; }
         else break;
     }
-    return false;
+    return 0;
 }
 
-template <int MC_WARPS>
-__global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(McParams P) {
+// WPS = resident warps per SM the register allocation is held to: 24 (<= 85 registers, no spills) or 32 (<= 64 registers,
+// ~120 B of spills per thread; the traversal is latency-bound, so a third more warps can pay for them: dm_tune "mc_occupancy")
+template <int MC_WARPS, int WPS>
+__global__ void __launch_bounds__(MC_WARPS * 32, WPS / MC_WARPS) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
     __shared__ PixState s_px[MC_WARPS];
@@ -464,9 +469,13 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
                     }
                     need = mask != 0ull;
                 }
-                if (!defer && need) {         // (3) undeferred: divergent descent right here
-                    hit = anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi);
-                    need = false;
+                if (need && (!defer || P.defer > 1)) {
+                    // (3) divergent descent right here -- P.defer > 1: for at most that many node steps; the few rays that
+                    // need more (the descent lengths are heavy-tailed: the slowest of 32 lanes takes ~6x the mean, which is
+                    // what held the warp at 5 / 32 lanes) are re-queued and finished together in phase B
+                    const int st_ = anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi, (defer && P.defer > 1) ? P.defer : 0x7fffffff);
+                    hit = st_ == 1;
+                    need = st_ == 2;
                 }
             } else if (valid) {
                 float bt, bu, bvv; int bid;
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, 24 / MC_WARPS) shade_mc_kernel(
                 const f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
                 const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
                 const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-                if (anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi)) mark_hit(s);
+                if (anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi, 0x7fffffff) == 1) mark_hit(s);
                 else shade_sample(s, d);
             }
         }
@@ -807,6 +816,7 @@ static int g_mc_frontier = 1;     // dm_tune "mc_frontier": 0 root traversal | 1
 static int g_mc_persistent = 0;   // dm_tune "mc_persistent": 1 = persistent warps with a static pixel interleave (measured slower:
                                   // per-pixel cost varies ~1:5, the hardware's CTA scheduler balances better), 0 = one CTA per MC_WARPS pixels
 static int g_mc_warps = 8;        // dm_tune "mc_warps": pixels (warps) per CTA, 1 | 2 | 4 | 8
+static int g_mc_occupancy = 24;   // dm_tune "mc_occupancy": 24 | 32 resident warps per SM (register budget 85 | 64)
 static int g_mc_defer = 0;        // dm_tune "mc_defer": 1 = compact the rays that need the divergent descent before descending (measured
                                   // SLOWER, 13.1 vs 9.2 ms: nearly every ray needs some descent, the lanes idle because descent lengths
                                   // differ, not because few rays enter; kept as a knob, profiles/r02_shade_frontier.md)
@@ -819,6 +829,10 @@ extern "C" int dm_tune(const char* key, int value) {
     else if (!strcmp(key, "mc_frontier")) g_mc_frontier = value;
     else if (!strcmp(key, "mc_persistent")) g_mc_persistent = value;
     else if (!strcmp(key, "mc_defer")) g_mc_defer = value;
+    else if (!strcmp(key, "mc_occupancy")) {
+        if (value != 24 && value != 32) { dm_set_error("dm_tune mc_occupancy: 24 or 32"); return DM_EINVAL; }
+        g_mc_occupancy = value;
+    }
     else if (!strcmp(key, "mc_warps")) {
         if (value != 1 && value != 2 && value != 4 && value != 8) { dm_set_error("dm_tune mc_warps: 1, 2, 4 or 8"); return DM_EINVAL; }
         g_mc_warps = value;
@@ -857,40 +871,44 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
 }
 
 namespace {
-template <int W>
+template <int W, int WPS>
 int launch_mc_w(const McParams& P, cudaStream_t st) {
-    // direction tables + one compacted sample-id list per warp
+    // direction tables + one compacted sample-id list per warp (+ the deferred-ray work list when that mode is on)
     const size_t S_ = (size_t)(P.cfg.n_diffuse + P.cfg.n_specular);
     const size_t smem = (size_t)(3 * P.cfg.n_diffuse + 2 * P.cfg.n_specular) * sizeof(float) + (size_t)W * S_ * sizeof(uint16_t) + 8 +
-                        (size_t)W * S_ * (sizeof(unsigned long long) + sizeof(unsigned short));
+                        (P.defer ? (size_t)W * S_ * (sizeof(unsigned long long) + sizeof(unsigned short)) : 0);
     static size_t smem_configured = 0;
     if (smem > smem_configured) {
-        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_configured = smem;
     }
     int64_t blocks = dm_ceil_div(P.n, W);
     if (g_mc_persistent) {
         static int per_sm = 0;
         if (!per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel<W>, W * 32, smem) != cudaSuccess || per_sm < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel<W, WPS>, W * 32, smem) != cudaSuccess || per_sm < 1) {
                 cudaGetLastError(); per_sm = 2;
             }
         }
         const int64_t resident = (int64_t)DM_NUM_SMS * per_sm;
         if (blocks > resident) blocks = resident;
     }
-    shade_mc_kernel<W><<<(unsigned)blocks, W * 32, smem, st>>>(P);
+    shade_mc_kernel<W, WPS><<<(unsigned)blocks, W * 32, smem, st>>>(P);
     return DM_OK;
 }
 }  // namespace
 
 static int launch_mc(const McParams& P, cudaStream_t st) {
     int rc;
-    switch (g_mc_warps) {
-        case 1: rc = launch_mc_w<1>(P, st); break;
-        case 2: rc = launch_mc_w<2>(P, st); break;
-        case 4: rc = launch_mc_w<4>(P, st); break;
-        default: rc = launch_mc_w<8>(P, st); break;
+    if (g_mc_occupancy == 32) {
+        rc = g_mc_warps == 4 ? launch_mc_w<4, 32>(P, st) : launch_mc_w<8, 32>(P, st);
+    } else {
+        switch (g_mc_warps) {
+            case 1: rc = launch_mc_w<1, 24>(P, st); break;
+            case 2: rc = launch_mc_w<2, 24>(P, st); break;
+            case 4: rc = launch_mc_w<4, 24>(P, st); break;
+            default: rc = launch_mc_w<8, 24>(P, st); break;
+        }
     }
     if (rc) return rc;
     DM_CHECK_LAUNCH();

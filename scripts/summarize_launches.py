@@ -25,7 +25,9 @@ def main():
     if not ends:
         print("no adam_kernel launch: cannot delimit a step"); return
     b = ends[which] + 1
-    a = max(i for i in starts if i < b)
+    prev = [e for e in ends if e < ends[which]]
+    # a step opens with the canvas fill that follows the previous step's Adam (fill_kernel also zeroes the CSD sums mid-step)
+    a = min((i for i in starts if i > prev[-1]), default=prev[-1] + 1) if prev else min(starts)
     step = rows[a:b]
     agg = defaultdict(lambda: [0, 0.0])
     for k, g, ms in step:

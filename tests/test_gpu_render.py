@@ -294,7 +294,7 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
     rd, rs = t(sc["rand_d"]).view(-1), t(sc["rand_s"]).view(-1)
     outs = []
     try:
-        for fr, pe, wp, df in ((0, 0, 8, 0), (1, 0, 8, 0), (1, 1, 8, 0), (64, 0, 8, 0), (1, 0, 8, 1), (48, 0, 2, 1), (0, 1, 4, 1), (1, 0, 1, 1)):
+        for fr, pe, wp, df in ((0, 0, 8, 0), (1, 0, 8, 0), (1, 1, 8, 0), (64, 0, 8, 0), (1, 0, 8, 1), (1, 0, 8, 16), (48, 0, 2, 4), (0, 1, 4, 1), (1, 0, 1, 1)):
             lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe); lib().dm_tune(b"mc_warps", wp); lib().dm_tune(b"mc_defer", df)
             color, jac, reg = torch.empty(n, 3, device=dev), torch.empty(n, 9, device=dev), torch.zeros(2, device=dev)
             bits = torch.zeros(n, (328 + 31) // 32, device=dev, dtype=torch.int32)
