@@ -816,7 +816,7 @@ static int g_mc_frontier = 1;     // dm_tune "mc_frontier": 0 root traversal | 1
 static int g_mc_persistent = 0;   // dm_tune "mc_persistent": 1 = persistent warps with a static pixel interleave (measured slower:
                                   // per-pixel cost varies ~1:5, the hardware's CTA scheduler balances better), 0 = one CTA per MC_WARPS pixels
 static int g_mc_warps = 8;        // dm_tune "mc_warps": pixels (warps) per CTA, 1 | 2 | 4 | 8
-static int g_mc_occupancy = 24;   // dm_tune "mc_occupancy": 24 | 32 resident warps per SM (register budget 85 | 64)
+static int g_mc_occupancy = 32;   // dm_tune "mc_occupancy": 24 | 32 resident warps per SM (register budget 85 | 64 with ~120 B of spills): 32 measured 3-4 % faster
 static int g_mc_defer = 0;        // dm_tune "mc_defer": 1 = compact the rays that need the divergent descent before descending (measured
                                   // SLOWER, 13.1 vs 9.2 ms: nearly every ray needs some descent, the lanes idle because descent lengths
                                   // differ, not because few rays enter; kept as a knob, profiles/r02_shade_frontier.md)

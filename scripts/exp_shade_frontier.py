@@ -38,4 +38,4 @@ for vid in (3, 40):
         ms = e0.elapsed_time(e1) / 5
         if ref is None: ref = col.clone()
         print(f"view {vid} pn={n} frontier={fr:2d} warps/CTA={warps} defer={df:2d} occupancy={occ}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  max|dcol| vs first {float((col - ref).abs().max()):.1e}")
-lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_warps", 8); lib().dm_tune(b"mc_defer", 0); lib().dm_tune(b"mc_occupancy", 24)
+lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_warps", 8); lib().dm_tune(b"mc_defer", 0); lib().dm_tune(b"mc_occupancy", 32)
