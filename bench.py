@@ -398,9 +398,13 @@ def splitsum_kernel_roofline(sysm, hbm):
 def gradient_identity_check(sysm, make_batch, cam_dev, V, world, rank, device):
     """--check: one step with explicit randomness (identical on every rank) computed (a) sharded over the ranks as in the
     timed loop -- views split, pixel-balanced shading if enabled, gradient all-reduce -- and (b) by rank 0 alone over the whole
-    global batch; the flat parameter gradients must agree (sum over views is the only cross-view coupling)."""
+    global batch; the flat parameter gradients must agree (the sum over views is the only cross-view coupling).  Done twice:
+    in the timed precision (fp16: two evaluations batch the networks differently, so they agree to the fp16 run-to-run
+    noise, which is measured alongside) and with the dense half in the fp32 high-precision mode (a crisp identity)."""
     import torch
     import torch.distributed as dist
+    from dreammat_b200 import weights as Wt
+    from dreammat_b200.guidance import StableDiffusionLightGuidance
     geo, ren = sysm.geometry, sysm.renderer
     b, tot_pn, _ = make_batch("device")
     gvid = [int(v) for v in b["global_view_id"]]
@@ -410,7 +414,7 @@ def gradient_identity_check(sysm, make_batch, cam_dev, V, world, rank, device):
         n = ren._cache[v]["pn"]
         rng["rand_ang"].append(torch.rand(n, generator=g)); rng["normal_eps"].append(torch.randn(n, generator=g) * 0.05)
         rng["rand_d"].append(torch.rand(n, generator=g)); rng["rand_s"].append(torch.rand(n, generator=g))
-    h = b["condition_map"].shape[1] // 8 if "condition_map" in b else (512 if sysm.resize_to_vae else b["height"]) // 8
+    h = (512 if sysm.resize_to_vae else b["height"]) // 8
     rng.update(t=torch.randint(20, 981, (V,), generator=g), noise=torch.randn(V, 4, h, h, generator=g), vae_eps=torch.randn(V, 4, h, h, generator=g),
                indexed_by="global_view")
 
@@ -418,46 +422,61 @@ def gradient_identity_check(sysm, make_batch, cam_dev, V, world, rank, device):
         def __getitem__(self, i):
             return None
     state = (geo.params.clone(), sysm.m.clone(), sysm.v.clone(), sysm.global_step)
-    maps = sysm.guidance.graphs.maps if sysm.guidance.graphs is not None else None
+    maps = sysm.guidance.maps
 
-    def cond_for(vids, eids):
-        if maps is not None:
-            return maps.condition_map(vids, eids)
-        return torch.stack([torch.rand(8 * h, 8 * h, 22, device=device, generator=torch.Generator(device=device).manual_seed(1000 + int(v)))
-                            for v in vids])
-    # (a) sharded
-    b["rays_o"] = b["rays_d"] = _Rays()
-    b["condition_map"] = cond_for(b["view_id"], b["env_id"])
-    sysm.training_step_fused(b, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
-    g_sharded = geo.grads.clone()
-    geo.params.copy_(state[0]); sysm.m.copy_(state[1]); sysm.v.copy_(state[2]); sysm.global_step = state[3]
-    # (b) rank 0 alone, whole global batch
-    err = floor = None
-    if rank == 0:
-        ws, bal = sysm.world_size, sysm.balance_pixels
-        sysm.world_size, sysm.balance_pixels = 1, False
-        try:
-            vid, eid = b["global_view_id"], b["global_env_id"]
-            full = {"view_id": vid, "env_id": eid, "height": b["height"], "width": b["width"], "rays_o": _Rays(), "rays_d": _Rays()}
-            for k in ("mvp_mtx", "w2c", "elevation", "azimuth", "camera_distances"):
-                full[k] = cam_dev[k][vid]
-            full["condition_map"] = cond_for(vid, eid)
-            sysm.training_step_fused(full, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
-            g_single = geo.grads.clone()
-            err = float((g_sharded.double() - g_single.double()).norm() / (g_single.double().norm() + 1e-30))
-            # the same single-process evaluation once more: its own run-to-run noise (fp32 atomics in split-K / GroupNorm
-            # statistics / hash-grid scatter feed an fp16 network) is the floor the sharded result has to be read against
-            geo.params.copy_(state[0])
-            sysm.training_step_fused(full, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
-            floor = float((geo.grads.double() - g_single.double()).norm() / (g_single.double().norm() + 1e-30))
-        finally:
-            sysm.world_size, sysm.balance_pixels = ws, bal
+    def restore():
         geo.params.copy_(state[0]); sysm.m.copy_(state[1]); sysm.v.copy_(state[2]); sysm.global_step = state[3]
-    if world > 1:
-        dist.barrier()
-    return {"grad_rel_err": err, "single_process_run_to_run": floor if rank == 0 else None, "what": "flat [grid | W1 | W2] gradient of one step: %d ranks (views sharded, balanced shading %s, all-reduce) "
-            "vs rank 0 alone on the same global batch and randomness" % (world, "on" if sysm.balance_pixels else "off"),
-            "dtype_note": "dense half in fp16: the two evaluations batch the networks differently (views per launch), so agreement is at the fp16 run-to-run level"}
+
+    def one_precision():
+        # (a) sharded
+        b["rays_o"] = b["rays_d"] = _Rays()
+        b["condition_map"] = maps.condition_map(b["view_id"], b["env_id"])
+        sysm.training_step_fused(b, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
+        g_sharded = geo.grads.clone()
+        restore()
+        # (b) rank 0 alone, whole global batch (no collective inside: world_size is 1 for it)
+        err = floor = None
+        if rank == 0:
+            ws, bal = sysm.world_size, sysm.balance_pixels
+            sysm.world_size, sysm.balance_pixels = 1, False
+            try:
+                vid, eid = b["global_view_id"], b["global_env_id"]
+                full = {"view_id": vid, "env_id": eid, "height": b["height"], "width": b["width"], "rays_o": _Rays(), "rays_d": _Rays()}
+                for k in ("mvp_mtx", "w2c", "elevation", "azimuth", "camera_distances"):
+                    full[k] = cam_dev[k][vid]
+                full["condition_map"] = maps.condition_map(vid, eid)
+                sysm.training_step_fused(full, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
+                g_single = geo.grads.clone()
+                err = float((g_sharded.double() - g_single.double()).norm() / (g_single.double().norm() + 1e-30))
+                # the same single-process evaluation once more: its own run-to-run noise (fp32 atomics in split-K / GroupNorm
+                # statistics / hash-grid scatter) is the floor the sharded result has to be read against
+                restore()
+                sysm.training_step_fused(full, global_views=V, total_pn_global=tot_pn, rng=rng, apply_optimizer=False)
+                floor = float((geo.grads.double() - g_single.double()).norm() / (g_single.double().norm() + 1e-30))
+            finally:
+                sysm.world_size, sysm.balance_pixels = ws, bal
+            restore()
+        if world > 1:
+            dist.barrier()
+        return err, floor
+    err16, floor16 = one_precision()
+    # fp32 high-precision dense half (same seeded weights, half_precision_weights=false)
+    guid16 = sysm.guidance
+    ucfg, vcfg = Wt.UNetConfig(), Wt.VAEConfig()
+    gcfg = dict(guid16.cfg.__dict__, half_precision_weights=False)
+    guid32 = StableDiffusionLightGuidance(gcfg, ucfg, vcfg, Wt.random_unet(ucfg, device, 10), Wt.random_controlnet(ucfg, device, 11),
+                                          Wt.random_vae(vcfg, device, 12), device)
+    guid32.maps = maps
+    sysm.guidance = guid32
+    try:
+        err32, floor32 = one_precision()
+    finally:
+        sysm.guidance = guid16
+        del guid32
+        torch.cuda.empty_cache()
+    return {"grad_rel_err": err16, "single_process_run_to_run": floor16, "grad_rel_err_fp32_mode": err32, "single_process_run_to_run_fp32_mode": floor32,
+            "what": "flat [grid | W1 | W2] gradient of one step: %d ranks (views sharded, balanced shading %s, all-reduce) vs rank 0 alone on the "
+                    "same global batch and randomness; fp16 (the timed precision) and fp32 high-precision dense half" % (world, "on" if sysm.balance_pixels else "off")}
 
 
 # ------------------------------------------------------------------------------------------------ stock PyTorch CUDA arm

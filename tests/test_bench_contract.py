@@ -58,5 +58,6 @@ def test_multi_gpu_lines():
     for d in (d8, d2):      # --check: the sharded step's gradient equals the single-process one within its run-to-run noise
         pc = d["parity_check"]
         assert pc["grad_rel_err"] is not None and pc["grad_rel_err"] < max(3 * pc["single_process_run_to_run"], 2e-2)
+        assert pc["grad_rel_err_fp32_mode"] < 1e-3          # the crisp identity: fp32 high-precision dense half
     w = _line("r02_bench_8gpu_config4_64views.json")
     assert w["n_gpus"] == 8 and w["scaling"] == "weak" and w["config"]["views"] == 64
