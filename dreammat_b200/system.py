@@ -435,7 +435,11 @@ class DreamMat:
 
         batch: output of the data mirror, already on the device (condition_map [B,H,W,22] fp32, cameras, env_id,
         view_id).  `global_views` / `total_pn_global`: batch-wide normalisers when the views are sharded over
-        ranks (loss_sds is a mean over views, loss_mat_reg a mean over covered pixels of the whole batch)."""
+        ranks (loss_sds is a mean over views, loss_mat_reg a mean over covered pixels of the whole batch).
+        Multi-GPU: the GRADIENT is global (all-reduced); the returned scalars (`loss`, `loss_sds`, `grad_norm`) are this
+        rank's share of the global batch -- logging-only values, left un-reduced to keep the step at one large collective.
+        `comp_depth` (logging only: `control_types=['light']` never feeds it to the guidance) is normalised per view, the
+        B > 1 semantics of SURVEY.md row a0; the reference's single min/max over the batch only exists for B = 1."""
         geo, mat, ren, guid = self.geometry, self.material, self.renderer, self.guidance
         guid.update_step(0, self.global_step)
         lam_sds, lam_reg = self.C(self.cfg.loss["lambda_sds"]), self.C(self.cfg.loss["lambda_mat_reg"])
