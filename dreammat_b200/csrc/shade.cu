@@ -109,6 +109,7 @@ struct McParams {
     uint32_t* hit_bits;
     int skip_horizon;   // dm_tune knob
     int frontier;       // dm_tune "mc_frontier": shared-origin traversal (see origin_frontier below)
+    int refill;         // dm_tune "mc_refill": N > 0 = batched-refill traversal, idle lanes refill when fewer than N are busy
     int defer;          // dm_tune "mc_defer": 0 off | 1 every ray that needs a descent is compacted first (phase B of the sample loop)
                         // | N > 1 rays whose descent exceeds N node steps are re-queued and finished together in phase B
     const int32_t* perm;   // optional coherent visiting order of the samples ([nd] diffuse ids, then [ns] specular ids)
@@ -277,7 +278,7 @@ __device__ __forceinline__ int anyhit_subtrees(const BvhView& bv, const Frontier
 
 // WPS = resident warps per SM the register allocation is held to: 24 (<= 85 registers, no spills) or 32 (<= 64 registers,
 // ~120 B of spills per thread; the traversal is latency-bound, so a third more warps can pay for them: dm_tune "mc_occupancy")
-template <int MC_WARPS, int WPS>
+template <int MC_WARPS, int WPS, bool REFILL>
 __global__ void __launch_bounds__(MC_WARPS * 32, WPS / MC_WARPS) shade_mc_kernel(McParams P) {
     extern __shared__ float s_tab[];  // [nd*3 | ns*2]: (az0, sqrt(ue+1e-7), sqrt(1-ue+1e-7)) | (phi0, ue)
     __shared__ float s_in[MC_WARPS][20];
@@ -425,6 +426,125 @@ __global__ void __launch_bounds__(MC_WARPS * 32, WPS / MC_WARPS) shade_mc_kernel
             if (P.hit_bits) atomicOr(P.hit_bits + pix * ((S + 31) / 32) + (s >> 5), 1u << (s & 31));
         };
         const bool horizon_cull = P.skip_horizon && !P.spec_light && !P.hit_bits;
+        if constexpr (REFILL) {
+          if (!use_frontier) {     // frontier overflow for this pixel (never seen on the bench meshes): plain root traversal
+            for (int base = 0; base < count; base += 32) {
+                if (base + lane >= count) continue;
+                const int s = list[base + lane];
+                const D3 d = sample_dir(s);
+                const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+                if (horizon_cull && s >= nd && (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f) continue;
+                const f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
+                float bt, bu, bvv; int bid;
+                if (bvh_trace<true>(P.bvh, o, dv, bt, bid, bu, bvv)) mark_hit(s); else shade_sample(s, d);
+            }
+          } else {
+            // ---- batched-refill traversal.  The divergent descents are heavy-tailed (the slowest of 32 lanes takes ~6x the
+            // mean), which held the lock-step version at 5 / 32 active lanes there.  Here every lane carries its own ray
+            // (sample id, frontier mask, node stack); the warp descends leaf by leaf until fewer than `refill` lanes are still
+            // busy, then the idle lanes -- together -- shade / mark their finished rays, draw the next samples of the pixel
+            // and run the coherent tests (local triangles, frontier boxes) for them, and the descent resumes with a full warp.
+            int next = 0;                       // next unassigned slot of the sample list (warp-uniform)
+            int s_cur = 0, fin = 0;             // fin: 0 nothing pending, 1 finished unoccluded (shade it), 2 finished occluded
+            bool have = false;
+            unsigned long long rmask = 0ull;
+            int cur = 0, sp = 0;
+            int stack[DM_BVH_STACK];
+            f3 ro = mk3(0, 0, 0), rd3 = mk3(0, 0, 1), rinv = mk3(0, 0, 0), roi = mk3(0, 0, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            while (true) {
+                // -- finished rays of the last descent, all idle lanes together
+                if (fin == 1) shade_sample(s_cur, sample_dir(s_cur));
+                else if (fin == 2) mark_hit(s_cur);
+                fin = 0;
+                // -- refill
+                const unsigned need = __ballot_sync(0xffffffffu, !have);
+                const int my = next + __popc(need & lt);
+                bool got = !have && my < count;
+                next += __popc(need);
+                if (__any_sync(0xffffffffu, got)) {
+                    const int s = got ? list[my] : 0;
+                    const D3 d = sample_dir(s);
+                    const f3 dv = mk3(d.x.v, d.y.v, d.z.v);
+                    if (got && horizon_cull && s >= nd && (dv.x * px.n[0] + dv.y * px.n[1] + dv.z * px.n[2]) <= 0.0f) got = false;
+                    const f3 o = mk3(px.p[0] + dv.x * 1e-5f, px.p[1] + dv.y * 1e-5f, px.p[2] + dv.z * 1e-5f);
+                    bool hit = false;
+                    for (int li = 0; li < FR.nl; ++li) {
+                        const int code = ~FR.leaf[li];
+                        const int first = code >> 2, cnt = (code & 3) + 1;
+                        for (int k = 0; k < cnt; ++k) {
+                            const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
+                            const float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+                            float u, v;
+                            if (got && !hit && tri_hit_pre(o, dv, A, B, C, u, v) < DM_RT_MAX_DIST) hit = true;
+                        }
+                    }
+                    const f3 inv = mk3(1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z);
+                    const f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+                    unsigned long long mask = 0ull;
+                    if (got && !hit) {
+                        for (int i = 0; i < FR.nf; ++i) {
+                            float tn;
+                            if (slab2(FR.box[i][0], FR.box[i][1], FR.box[i][2], FR.box[i][3], FR.box[i][4], FR.box[i][5], inv, oi,
+                                      DM_RT_MAX_DIST, tn)) mask |= 1ull << i;
+                        }
+                    }
+                    if (got) {
+                        if (hit) mark_hit(s);
+                        else if (mask == 0ull) shade_sample(s, d);
+                        else {
+                            have = true; s_cur = s; ro = o; rd3 = dv; rinv = inv; roi = oi; sp = 0;
+                            const int i = __ffsll((long long)mask) - 1;
+                            cur = FR.code[i]; rmask = mask & (mask - 1ull);
+                        }
+                    }
+                }
+                const unsigned act0 = __ballot_sync(0xffffffffu, have);
+                if (act0 == 0u) { if (next >= count) break; continue; }
+                // -- descent, one leaf at a time, until too few lanes are busy (or to the end once the list is exhausted)
+                const int thresh = next >= count ? 1 : P.refill;
+                while (true) {
+                    if (have) {
+                        bool alive = true;
+                        while (alive && cur >= 0) {           // down to the next leaf (or out of work)
+                            const float4* n = P.bvh.nodes + (int64_t)cur * 4;
+                            float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+                            float tl, tr;
+                            bool hl = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rinv, roi, DM_RT_MAX_DIST, tl);
+                            bool hr = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rinv, roi, DM_RT_MAX_DIST, tr);
+                            int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+                            if (hl && hr) {
+                                bool lfirst = tl <= tr;
+                                if (sp < DM_BVH_STACK) stack[sp++] = lfirst ? cr : cl;
+                                cur = lfirst ? cl : cr;
+                            } else if (hl) cur = cl;
+                            else if (hr) cur = cr;
+                            else if (sp > 0) cur = stack[--sp];
+                            else if (rmask) { const int i = __ffsll((long long)rmask) - 1; rmask &= rmask - 1ull; cur = FR.code[i]; }
+                            else alive = false;
+                        }
+                        if (!alive) { have = false; fin = 1; }
+                        else {
+                            const int code = ~cur;
+                            const int first = code >> 2, cnt = (code & 3) + 1;
+                            bool hit = false;
+                            for (int k = 0; k < cnt; ++k) {
+                                const float4* tp = P.bvh.tris + (int64_t)(first + k) * 3;
+                                float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+                                float u, v;
+                                if (tri_hit_pre(ro, rd3, A, B, C, u, v) < DM_RT_MAX_DIST) hit = true;
+                            }
+                            if (hit) { have = false; fin = 2; }
+                            else if (sp > 0) cur = stack[--sp];
+                            else if (rmask) { const int i = __ffsll((long long)rmask) - 1; rmask &= rmask - 1ull; cur = FR.code[i]; }
+                            else { have = false; fin = 1; }
+                        }
+                    }
+                    if (__popc(__ballot_sync(0xffffffffu, have)) < thresh) break;
+                }
+            }
+          }
+        } else {
         // ---- phase A (lane = slot of the work list, all lanes in step).  Samples are visited in table order (Fibonacci points
         // sorted by elevation).  With the frontier: local triangles and frontier boxes are tested here, coherently; a ray
         // that is neither occluded by a local triangle nor clear of every frontier box is DEFERRED: (sample id, box mask)
@@ -507,6 +627,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32, WPS / MC_WARPS) shade_mc_kernel
                 if (anyhit_subtrees(P.bvh, FR, mask, o, dv, inv, oi, 0x7fffffff) == 1) mark_hit(s);
                 else shade_sample(s, d);
             }
+        }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -817,6 +938,7 @@ static int g_mc_persistent = 0;   // dm_tune "mc_persistent": 1 = persistent war
                                   // per-pixel cost varies ~1:5, the hardware's CTA scheduler balances better), 0 = one CTA per MC_WARPS pixels
 static int g_mc_warps = 8;        // dm_tune "mc_warps": pixels (warps) per CTA, 1 | 2 | 4 | 8
 static int g_mc_occupancy = 32;   // dm_tune "mc_occupancy": 24 | 32 resident warps per SM (register budget 85 | 64 with ~120 B of spills): 32 measured 3-4 % faster
+static int g_mc_refill = 0;       // dm_tune "mc_refill": 0 lock-step passes | N in 1..32: per-lane rays, refill when fewer than N lanes descend
 static int g_mc_defer = 0;        // dm_tune "mc_defer": 1 = compact the rays that need the divergent descent before descending (measured
                                   // SLOWER, 13.1 vs 9.2 ms: nearly every ray needs some descent, the lanes idle because descent lengths
                                   // differ, not because few rays enter; kept as a knob, profiles/r02_shade_frontier.md)
@@ -829,6 +951,7 @@ extern "C" int dm_tune(const char* key, int value) {
     else if (!strcmp(key, "mc_frontier")) g_mc_frontier = value;
     else if (!strcmp(key, "mc_persistent")) g_mc_persistent = value;
     else if (!strcmp(key, "mc_defer")) g_mc_defer = value;
+    else if (!strcmp(key, "mc_refill")) g_mc_refill = value < 0 ? 0 : (value > 32 ? 32 : value);
     else if (!strcmp(key, "mc_occupancy")) {
         if (value != 24 && value != 32) { dm_set_error("dm_tune mc_occupancy: 24 or 32"); return DM_EINVAL; }
         g_mc_occupancy = value;
@@ -867,11 +990,12 @@ extern "C" int dm_shade_mc_fwd(const dm_material_cfg* cfg, const dm_bvh* bvh, co
     P.skip_horizon = g_mc_skip_horizon;
     P.frontier = g_mc_frontier;
     P.defer = g_mc_defer;
+    P.refill = g_mc_refill;
     return launch_mc(P, (cudaStream_t)stream);
 }
 
 namespace {
-template <int W, int WPS>
+template <int W, int WPS, bool RF = false>
 int launch_mc_w(const McParams& P, cudaStream_t st) {
     // direction tables + one compacted sample-id list per warp (+ the deferred-ray work list when that mode is on)
     const size_t S_ = (size_t)(P.cfg.n_diffuse + P.cfg.n_specular);
@@ -879,28 +1003,30 @@ int launch_mc_w(const McParams& P, cudaStream_t st) {
                         (P.defer ? (size_t)W * S_ * (sizeof(unsigned long long) + sizeof(unsigned short)) : 0);
     static size_t smem_configured = 0;
     if (smem > smem_configured) {
-        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DM_CHECK_CUDA(cudaFuncSetAttribute(shade_mc_kernel<W, WPS, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_configured = smem;
     }
     int64_t blocks = dm_ceil_div(P.n, W);
     if (g_mc_persistent) {
         static int per_sm = 0;
         if (!per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel<W, WPS>, W * 32, smem) != cudaSuccess || per_sm < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_mc_kernel<W, WPS, RF>, W * 32, smem) != cudaSuccess || per_sm < 1) {
                 cudaGetLastError(); per_sm = 2;
             }
         }
         const int64_t resident = (int64_t)DM_NUM_SMS * per_sm;
         if (blocks > resident) blocks = resident;
     }
-    shade_mc_kernel<W, WPS><<<(unsigned)blocks, W * 32, smem, st>>>(P);
+    shade_mc_kernel<W, WPS, RF><<<(unsigned)blocks, W * 32, smem, st>>>(P);
     return DM_OK;
 }
 }  // namespace
 
 static int launch_mc(const McParams& P, cudaStream_t st) {
     int rc;
-    if (g_mc_occupancy == 32) {
+    if (g_mc_refill > 0 && g_mc_frontier > 0) {
+        rc = g_mc_occupancy == 32 ? launch_mc_w<8, 32, true>(P, st) : launch_mc_w<8, 24, true>(P, st);
+    } else if (g_mc_occupancy == 32) {
         rc = g_mc_warps == 4 ? launch_mc_w<4, 32>(P, st) : launch_mc_w<8, 32>(P, st);
     } else {
         switch (g_mc_warps) {

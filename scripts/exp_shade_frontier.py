@@ -23,8 +23,9 @@ for vid in (3, 40):
     rd, rs = torch.rand(n, device=dev, generator=gen), torch.rand(n, device=dev, generator=gen)
     ref = None
     bvh = R.Bvh(mesh[0], mesh[1])
-    for (fr, warps, df, occ) in ((0, 8, 0, 24), (1, 8, 0, 24), (1, 8, 0, 32), (1, 8, 8, 24), (1, 8, 12, 24), (1, 8, 16, 24), (1, 8, 24, 24), (1, 8, 32, 24),
-                                 (1, 8, 48, 24), (1, 8, 16, 32), (1, 8, 24, 32), (1, 4, 16, 24), (32, 8, 16, 24)):
+    for (fr, warps, df, occ, rf) in ((0, 8, 0, 24, 0), (1, 8, 0, 24, 0), (1, 8, 0, 32, 0), (1, 8, 0, 24, 8), (1, 8, 0, 24, 16), (1, 8, 0, 24, 20), (1, 8, 0, 24, 24),
+                                     (1, 8, 0, 24, 28), (1, 8, 0, 24, 32), (1, 8, 0, 32, 16), (1, 8, 0, 32, 24), (1, 8, 0, 32, 32)):
+        lib().dm_tune(b"mc_refill", rf)
         lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_warps", warps); lib().dm_tune(b"mc_defer", df); lib().dm_tune(b"mc_occupancy", occ)
         def run():
             return R.shade_mc(f, fj, g["pts"], g["nrm"], g["vd"], rd, rs, mat.mc_cfg, bvh, mat.light[0], mat.tab_d,
@@ -37,5 +38,5 @@ for vid in (3, 40):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         if ref is None: ref = col.clone()
-        print(f"view {vid} pn={n} frontier={fr:2d} warps/CTA={warps} defer={df:2d} occupancy={occ}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  max|dcol| vs first {float((col - ref).abs().max()):.1e}")
-lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_warps", 8); lib().dm_tune(b"mc_defer", 0); lib().dm_tune(b"mc_occupancy", 32)
+        print(f"view {vid} pn={n} frontier={fr:2d} warps/CTA={warps} defer={df:2d} occupancy={occ} refill={rf:2d}: {ms:.3f} ms  {n*328/ms/1e6:.2f} Grays/s  max|dcol| vs first {float((col - ref).abs().max()):.1e}")
+lib().dm_tune(b"mc_frontier", 1); lib().dm_tune(b"mc_warps", 8); lib().dm_tune(b"mc_defer", 0); lib().dm_tune(b"mc_occupancy", 32); lib().dm_tune(b"mc_refill", 0)

@@ -273,7 +273,7 @@ def test_resize_bilinear_matches_torch(ops):
         assert rel_err(xc.grad.cpu(), xr.grad) < 1e-5
 
 
-DEFAULT_FRONTIER, DEFAULT_WARPS = 1, 8     # library defaults (csrc/shade.cu g_mc_frontier / g_mc_warps)
+DEFAULT_FRONTIER, DEFAULT_WARPS, DEFAULT_REFILL = 1, 8, 0     # library defaults (csrc/shade.cu g_mc_frontier / g_mc_warps / g_mc_refill)
 
 
 def test_frontier_traversal_is_bit_identical_to_root_traversal():
@@ -294,8 +294,10 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
     rd, rs = t(sc["rand_d"]).view(-1), t(sc["rand_s"]).view(-1)
     outs = []
     try:
-        for fr, pe, wp, df in ((0, 0, 8, 0), (1, 0, 8, 0), (1, 1, 8, 0), (64, 0, 8, 0), (1, 0, 8, 1), (1, 0, 8, 16), (48, 0, 2, 4), (0, 1, 4, 1), (1, 0, 1, 1)):
+        for fr, pe, wp, df, rf in ((0, 0, 8, 0, 0), (1, 0, 8, 0, 0), (1, 1, 8, 0, 0), (64, 0, 8, 0, 0), (1, 0, 8, 1, 0), (1, 0, 8, 16, 0), (48, 0, 2, 4, 0),
+                                   (0, 1, 4, 1, 0), (1, 0, 1, 1, 0), (1, 0, 8, 0, 16), (1, 0, 8, 0, 32), (48, 0, 8, 0, 4)):
             lib().dm_tune(b"mc_frontier", fr); lib().dm_tune(b"mc_persistent", pe); lib().dm_tune(b"mc_warps", wp); lib().dm_tune(b"mc_defer", df)
+            lib().dm_tune(b"mc_refill", rf)
             color, jac, reg = torch.empty(n, 3, device=dev), torch.empty(n, 9, device=dev), torch.zeros(2, device=dev)
             bits = torch.zeros(n, (328 + 31) // 32, device=dev, dtype=torch.int32)
             check(lib().dm_shade_mc_fwd(C.byref(cfg), bvh.h, ptr(env), env.shape[0], env.shape[1], ptr(tab_d), ptr(tab_s), ptr(pts),
@@ -304,7 +306,7 @@ def test_frontier_traversal_is_bit_identical_to_root_traversal():
             outs.append((color, jac, bits, reg))
     finally:
         lib().dm_tune(b"mc_frontier", DEFAULT_FRONTIER); lib().dm_tune(b"mc_persistent", 0); lib().dm_tune(b"mc_warps", DEFAULT_WARPS)
-        lib().dm_tune(b"mc_defer", 0)
+        lib().dm_tune(b"mc_defer", 0); lib().dm_tune(b"mc_refill", DEFAULT_REFILL)
     occ = int(sum(bin(int(x) & 0xffffffff).count("1") for x in outs[0][2].flatten()[:4096].tolist()))
     assert occ > 0                      # the bumpy mesh self-occludes: the comparison is not vacuous
     for i, (color, jac, bits, reg) in enumerate(outs[1:], 1):
