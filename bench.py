@@ -180,6 +180,7 @@ def run_ours(args):
     gres = 512 if sysm.resize_to_vae else res                    # renders that are not 512^2 are resized before the VAE
     # N1: the pre-rendered condition maps (depth fp32, normal / 6 light maps uint8; data/uncond.py:532-582) live on the device
     # -- 3.3 GB for 128 views x 5 envs at 512^2 -- and are gathered + de-quantised inside the ControlNet graph by (view, env) id
+    from dreammat_b200.parallel import global_pixel_count, shard_slice
     from dreammat_b200.scene import FixViewMaps
     n_fix, n_env = cams.cfg.fix_view_num, 5
     maps = FixViewMaps.synthetic(n_fix, n_env, gres, gres, device=device, seed=7)
@@ -210,8 +211,8 @@ def run_ours(args):
     def make_batch(mode):
         """mode: 'device' (ids + cameras already resident) | 'e2e' (this step's ids + camera tensors come from pinned host memory)"""
         view_id, env_id = cams.collate(gsel, V)
-        tot_pn = int(sum(pn[int(v)] for v in view_id))
-        mine = slice(rank * Vl, (rank + 1) * Vl)
+        tot_pn = global_pixel_count(pn, view_id)
+        mine = shard_slice(V, rank, world)
         vid, eid = view_id[mine], env_id[mine]
         b = {"view_id": vid, "env_id": eid, "height": res, "width": res, "global_view_id": view_id, "global_env_id": env_id}
         h2d = 0

@@ -594,9 +594,8 @@ class DreamMat:
                 check(lib().dm_hashgrid_mlp_bwd(C.byref(geo.hg), ptr(pts_), n, ptr(geo.grid), ptr(geo.W1), ptr(geo.W2), ptr(d_),
                                                 ptr(geo.dgrid), ptr(geo.dW1), ptr(geo.dW2), st), "hashgrid bwd")
         loss_reg = (0.25 * reg_sums[0] + 0.1 * reg_sums[1]) / total_pn
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(geo.grads, op=dist.ReduceOp.SUM)     # the single collective of the step (NVLink / NVSwitch)
+        from .parallel import allreduce_gradients
+        allreduce_gradients(geo.grads, self.world_size)          # the single large collective of the step (NVLink / NVSwitch)
         if apply_optimizer:       # False: the host framework (Lightning) steps its own optimizer on the same flat gradient
             self.optimizer_step()
         self._mark("render_bwd_adam")
