@@ -180,7 +180,7 @@ def run_ours(args):
     gres = 512 if sysm.resize_to_vae else res                    # renders that are not 512^2 are resized before the VAE
     # N1: the pre-rendered condition maps (depth fp32, normal / 6 light maps uint8; data/uncond.py:532-582) live on the device
     # -- 3.3 GB for 128 views x 5 envs at 512^2 -- and are gathered + de-quantised inside the ControlNet graph by (view, env) id
-    from dreammat_b200.parallel import global_pixel_count, shard_slice
+    from dreammat_b200.parallel import global_pixel_count, quiesce_host_gc, shard_slice
     from dreammat_b200.scene import FixViewMaps
     n_fix, n_env = cams.cfg.fix_view_num, 5
     maps = FixViewMaps.synthetic(n_fix, n_env, gres, gres, device=device, seed=7)
@@ -246,6 +246,8 @@ def run_ours(args):
     def timed(n_warm, n_steps, mode):
         for _ in range(n_warm):
             step(mode)
+        if not args.no_gc_freeze:
+            quiesce_host_gc()      # what the plugin does in on_fit_start: no 30-40 ms full-GC pause on any rank inside a step
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -265,7 +267,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         l1 = _cabi.lib().dm_launch_count() + (gr.replayed_launches if gr else 0)
         per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n_steps))
-        spread = {"median_ms": per[len(per) // 2], "min_ms": per[0], "max_ms": per[-1]}
+        spread = {"median_ms": per[len(per) // 2], "min_ms": per[0], "max_ms": per[-1],
+                  "steps_over_1p5x_median": sum(1 for x in per if x > 1.5 * per[len(per) // 2])}
         return float(ms) / n_steps, (l1 - l0) // n_steps, spread
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -738,6 +741,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the dense kernels")
+    ap.add_argument("--no-gc-freeze", action="store_true", help="A/B: leave Python's full collections inside the timed region")
     ap.add_argument("--no-balance", action="store_true", help="multi-GPU: every rank shades only its own views")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner, nvcc/ninja chatter)

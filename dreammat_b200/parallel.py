@@ -14,9 +14,20 @@ Normalisation that keeps the sharded step equal to the single-process one:
 """
 from __future__ import annotations
 
+import gc
 from typing import List, Sequence, Tuple
 
 import torch
+
+
+def quiesce_host_gc() -> None:
+    """Move everything alive now (torch, the nets, the scene: ~170 k objects) to the permanent generation.  With one process per
+    GPU every step ends in a collective, so the step is as slow as the slowest rank's HOST: a full generation-2 collection of
+    this process takes 32-40 ms (measured), longer than the whole 8-GPU step (25 ms), and on 8 ranks it hits some rank every
+    few steps.  After the freeze a full collection only walks what was allocated since (microseconds).  No reference counterpart
+    (Lightning DDP pays the same pause; at ~1 s / iteration it does not show)."""
+    gc.collect()
+    gc.freeze()
 
 
 def shard_slice(n_views: int, rank: int, world: int) -> slice:

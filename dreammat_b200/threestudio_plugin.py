@@ -325,6 +325,8 @@ class DreamMat(BaseLift3DSystem):
         impl = _Y.DreamMat({"loss": _plain(self.cfg.loss, ()), "optimizer": _plain(self.cfg.optimizer, ())}, self.geometry.impl,
                            self.material.impl, self.renderer.impl, g, None, device=self.geometry.impl.device)
         object.__setattr__(self, "impl", impl)
+        from .parallel import quiesce_host_gc
+        quiesce_host_gc()
 
     def _log(self, name, value):
         try:
