@@ -256,9 +256,11 @@ def run_ours(args):
         l0 = _cabi.lib().dm_launch_count() + (gr.replayed_launches if gr else 0)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
         ev[0].record()
+        host, seg0 = [time.perf_counter()], torch.cuda.memory_stats().get("num_device_alloc", 0)
         for i in range(n_steps):
             step(mode)
             ev[i + 1].record()
+            host.append(time.perf_counter())
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -266,9 +268,13 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         l1 = _cabi.lib().dm_launch_count() + (gr.replayed_launches if gr else 0)
-        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n_steps))
+        raw = [ev[i].elapsed_time(ev[i + 1]) for i in range(n_steps)]
+        worst = max(range(n_steps), key=lambda i: raw[i])
+        per = sorted(raw)
         spread = {"median_ms": per[len(per) // 2], "min_ms": per[0], "max_ms": per[-1],
-                  "steps_over_1p5x_median": sum(1 for x in per if x > 1.5 * per[len(per) // 2])}
+                  "steps_over_1p5x_median": sum(1 for x in per if x > 1.5 * per[len(per) // 2]),
+                  "slowest_step": {"index": worst, "host_ms": (host[worst + 1] - host[worst]) * 1e3,
+                                   "cudaMalloc_calls_in_region": torch.cuda.memory_stats().get("num_device_alloc", 0) - seg0}}
         return float(ms) / n_steps, (l1 - l0) // n_steps, spread
 
     sampler = ClockSampler(local) if rank == 0 else None

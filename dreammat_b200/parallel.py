@@ -22,10 +22,11 @@ import torch
 
 def quiesce_host_gc() -> None:
     """Move everything alive now (torch, the nets, the scene: ~170 k objects) to the permanent generation.  With one process per
-    GPU every step ends in a collective, so the step is as slow as the slowest rank's HOST: a full generation-2 collection of
-    this process takes 32-40 ms (measured), longer than the whole 8-GPU step (25 ms), and on 8 ranks it hits some rank every
-    few steps.  After the freeze a full collection only walks what was allocated since (microseconds).  No reference counterpart
-    (Lightning DDP pays the same pause; at ~1 s / iteration it does not show)."""
+    GPU every step ends in a collective, so the step is as slow as the slowest rank's HOST, and a full generation-2 collection
+    of this process takes 32-40 ms (measured) against a 25 ms 8-GPU step.  After the freeze a full collection only walks what
+    was allocated since (microseconds).  Insurance, not a measured win: the 300-step A/B runs on 1 and 2 GPUs
+    (profiles/r02_exp_step_outliers.md) saw no step hit by a collection either way -- the step allocates few container objects.
+    No reference counterpart."""
     gc.collect()
     gc.freeze()
 
@@ -84,6 +85,25 @@ def pixel_partition(pn_global: Sequence[int], world: int) -> Tuple[List[List[Tup
         segments.append(segs)
         counts.append(cnt)
     return segments, counts
+
+
+def warm_exchange(max_rows: int, world: int, device) -> None:
+    """Run the row exchange once per message-size decade before the step loop.  NCCL sets up point-to-point channels lazily
+    and uses more of them for larger messages, while the per-step counts vary with the sampled views, so a size class first
+    seen inside the loop can pay a connection setup there.  A candidate for the single 350 ms step seen in one 300-step run on
+    2 GPUs (profiles/r02_exp_step_outliers.md); not separated from the allocator cause handled by
+    DreamMat.reserve_step_scratch()."""
+    if world == 1:
+        return
+    rows = 16
+    while True:
+        rows = min(rows, max(int(max_rows), 16))
+        for c in (3, 9):
+            buf = torch.zeros(rows * world, c, device=device)
+            exchange_rows(buf, [rows] * world, [rows] * world, world)
+        if rows >= max_rows:
+            break
+        rows *= 4
 
 
 def exchange_rows(send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int], world: int) -> torch.Tensor:
