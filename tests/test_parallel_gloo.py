@@ -134,6 +134,11 @@ def _a2a_worker(rank, world, port, ret):
     ok = torch.equal(own[:, 0], torch.arange(lo, hi, dtype=torch.float32))
     back = exchange_rows(own * 2, recv_counts, counts[rank], world)           # the backward direction
     ok = ok and torch.equal(back, send * 2)
+    from dreammat_b200.parallel import warm_exchange
+    warm_exchange(1000, world, "cpu")         # size ladder 16, 64, 256, 1000: terminates, same collectives on every rank
+    warm_exchange(3, world, "cpu")
+    again = exchange_rows(send, counts[rank], recv_counts, world)             # and leaves the exchange usable
+    ok = ok and torch.equal(again, own)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
