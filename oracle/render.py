@@ -560,17 +560,18 @@ def fg_lookup(lut, ndv, rough):
             lut[y1, x1] * fx * fy)
 
 
-def shade_splitsum(normals, viewdirs, diffuse_cube, spec_mips, lut, metallic, roughness, albedo):
-    """dreammat_material.py:679-711."""
+def shade_splitsum_with(normals, viewdirs, fg_fn, diffuse_fn, specular_fn, metallic, roughness, albedo):
+    """dreammat_material.py:679-711 with its three texture fetches as callables: `fg_fn(n.v, roughness) -> [N,2]`
+    (dr.texture on FG_LUT), `diffuse_fn(n) -> [N,3]` and `specular_fn(r, roughness) -> [N,3]` (the envlight object).
+    Pinned against the reference's own `shade_splitsum` body by tests/golden/make_splitsum_golden.py."""
     v = viewdirs
     n_dot_v = (normals * v).sum(-1, keepdim=True)
     reflective = n_dot_v * normals * 2 - v
-    fg = fg_lookup(lut, n_dot_v[..., 0], roughness[..., 0])
+    fg = fg_fn(n_dot_v[..., 0], roughness[..., 0])
     F0 = (1 - metallic) * 0.04 + metallic * albedo
     specular_albedo = F0 * fg[:, 0:1] + fg[:, 1:2]
-    diffuse_light = cube_sample_linear(diffuse_cube, normals)
-    level = envlight_mip_level(roughness[..., 0], len(spec_mips))
-    specular_light = cube_sample_trilinear(spec_mips, reflective, level)
+    diffuse_light = diffuse_fn(normals)
+    specular_light = specular_fn(reflective, roughness)
     color = (albedo * diffuse_light + specular_albedo * specular_light).clamp(0.0, 1.0)
     return {
         "color": color,
@@ -582,6 +583,14 @@ def shade_splitsum(normals, viewdirs, diffuse_cube, spec_mips, lut, metallic, ro
         "specular_colors": lin2srgb(specular_albedo.detach()),
         "diffuse_colors": lin2srgb(albedo.detach()),
     }
+
+
+def shade_splitsum(normals, viewdirs, diffuse_cube, spec_mips, lut, metallic, roughness, albedo):
+    """dreammat_material.py:679-711 over the oracle's own envlight restatement (cube maps) and FG lookup."""
+    return shade_splitsum_with(
+        normals, viewdirs, lambda ndv, r: fg_lookup(lut, ndv, r), lambda n: cube_sample_linear(diffuse_cube, n),
+        lambda d, r: cube_sample_trilinear(spec_mips, d, envlight_mip_level(r[..., 0], len(spec_mips))),
+        metallic, roughness, albedo)
 
 
 # ----------------------------------------------------------------------------- cameras / G-buffer (a1, a2)

@@ -32,3 +32,14 @@ def make_scene(res=48, subdiv=3, bump=0.12, seed=0, n_views=1):
 def rel_err(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def analytic_envlight(l, roughness=None):
+    """Smooth positive stand-in for `envlight.EnvLight.__call__(l, roughness=None)` (third-party, absent): diffuse irradiance
+    for `roughness is None`, prefiltered radiance otherwise.  Used by tests/golden/make_splitsum_golden.py when it executes the
+    reference's shade_splitsum, and by the test that replays the same inputs through the oracle."""
+    a = torch.tensor([[0.9, 0.2, -0.3], [0.1, 0.8, 0.4], [-0.5, 0.3, 0.7]], dtype=l.dtype)
+    base = 0.8 + 0.5 * torch.sin(l @ a + torch.tensor([0.3, 1.1, 2.0], dtype=l.dtype))
+    if roughness is None:
+        return base
+    return base * (1.2 - 0.8 * roughness) + 0.15 * roughness * roughness
