@@ -720,6 +720,34 @@ def jitter_positions(positions, normals, rand_ang, normal_eps):
     return positions + (torch.cos(ang) * x + torch.sin(ang) * y) * normal_eps
 
 
+def render_forward(gb, pairs, geometry_fn, material_fn, rand_ang, normal_eps):
+    """RaytraceRender.forward (raytracing_renderer.py:110-222) for ONE view (the reference's inline normal-map code only
+    reshapes for B = 1): G-buffer `gb` (gbuffer() above) -> tangent jitter -> geometry twice -> material -> canvases of
+    ones with the covered pixels written in -> antialias.  `pairs` = antialias_pairs() of the view; `geometry_fn(points)`
+    -> features; `material_fn(pts, features, features_jitter, viewdirs, normals)` -> (shade outputs, mat_reg).
+    Pinned against the reference's own forward by tests/golden/make_renderer_golden.py."""
+    B, H, W, _ = gb["rast"].shape
+    assert B == 1
+    sel = gb["selector"][0]
+    pos, nrm, vd = gb["gb_pos"][0][sel], gb["gb_normal"][0][sel], gb["gb_viewdirs"][0][sel]
+    f = geometry_fn(pos)
+    fj = geometry_fn(jitter_positions(pos, nrm, rand_ang, normal_eps))
+    shade, reg = material_fn(pos, f, fj, vd, nrm)
+    idx = (torch.nonzero(sel).view(-1),)
+
+    def canvas(v):
+        return torch.ones(H * W, v.shape[-1], dtype=v.dtype).index_put(idx, v)
+
+    def aa(img):
+        return antialias_apply(img.reshape(H * W, -1), pairs).reshape(1, H, W, -1)
+    out = {"comp_rgb": aa(canvas(shade["color"])), "opacity": aa(gb["mask"].float()), "comp_depth": gb["comp_depth"],
+           "comp_normal": aa(gb["comp_normal"]), "loss_mat_reg": reg}
+    for k_out, k_in in (("albedo", "albedo"), ("metalness", "metalness"), ("roughness", "roughness"), ("specular_light", "specular_lights"),
+                        ("diffuse_light", "diffuse_lights"), ("specular_color", "specular_colors"), ("diffuse_color", "diffuse_colors")):
+        out[k_out] = canvas(shade[k_in].detach()).reshape(1, H, W, -1)
+    return out
+
+
 # ----------------------------------------------------------------------------- procedural fixtures
 
 
