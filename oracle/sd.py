@@ -259,13 +259,18 @@ def sds_grad(eps_text, eps_uncond, eps_null, noise, t, ac, c, u, n, s):
 
 
 def guidance_step(wv, wc, wu, ucfg: UNetConfig, vcfg: VAEConfig, rgb_bhwc, cond_bhwc, ctx3, t, noise, vae_eps,
-                  scales=(1.05, -1.0, 0.0, 0.0), cond_scale=1.0, q: Callable = Ident, return_eps: bool = False):
+                  scales=(1.05, -1.0, 0.0, 0.0), cond_scale=1.0, q: Callable = Ident, return_eps: bool = False,
+                  resize_to=None):
     """StableDiffusionLightGuidance.__call__ (:536-602) for explicit randomness (appendix B #7-#9).
-    ctx3 [3B,77,D] ordered [text | uncond | null].  Returns (loss_sds, grad, latents[, eps [3,B,4,h,w]])."""
+    ctx3 [3B,77,D] ordered [text | uncond | null].  Returns (loss_sds, grad, latents[, eps [3,B,4,h,w]]).
+    `resize_to=(H, W)`: get_latents' rule (:507-513) -- a render whose height differs from cfg.height is resized to
+    (cfg.width, cfg.height) = 512 x 512 with bilinear / align_corners=False before the VAE (None: the oracle is also used at
+    reduced sizes, where the caller's render IS the VAE input).  Pinned against the reference's own __call__ by
+    tests/golden/make_guidance_golden.py."""
     B = rgb_bhwc.shape[0]
     x = rgb_bhwc.permute(0, 3, 1, 2)
-    if x.shape[-1] != 512 or x.shape[-2] != 512:
-        pass  # the oracle is also used at reduced sizes in tests; the reference resizes to 512 (:507-513)
+    if resize_to is not None and x.shape[2] != resize_to[0]:
+        x = F.interpolate(x, tuple(resize_to), mode="bilinear", align_corners=False)
     mom = vae_encode_moments(wv, vcfg, q(x * 2.0 - 1.0), q)
     z = vae_sample(mom, vae_eps, vcfg.scaling_factor, q)
     ac = alphas_cumprod()
