@@ -592,7 +592,9 @@ class DreamMat:
             check(lib().dm_resize_bilinear(ptr(dvae.contiguous()), B, H, W, 512, 512, 3, ptr(dcanvas), 1, st), "dm_resize_bilinear")
         else:
             dcanvas = dvae.reshape(B, H * W, 3)
-        gout = {"grad_norm": sums[1].sqrt()}
+        n = sums.sqrt()       # the reference logs all of these every step (systems/dreammat.py:72-74 over compute_grad_sds' dict)
+        gout = {"grad_norm": n[1], "uncond_m_noise_norm": n[2], "text_m_noise_norm": n[3], "text_m_uncond_norm": n[4],
+                "text_m_null_norm": n[5], "null_m_uncond_norm": n[6], "noise_norm": n[7], "uncond_norm": n[8], "text_norm": n[9]}
         # backward into the hash grid / MLP
         geo.grads.zero_()
         dcolor_own = torch.empty(max(own_px, 1), 3, device=dev)
@@ -625,4 +627,4 @@ class DreamMat:
             self.reserve_step_scratch()
         self._steps_fused += 1
         return {"loss": lam_sds * loss_sds.detach() + lam_reg * loss_reg, "loss_sds": loss_sds.detach(),
-                "loss_mat_reg": loss_reg, "comp_rgb": comp_rgb.detach(), "grad_norm": gout["grad_norm"]}
+                "loss_mat_reg": loss_reg, "comp_rgb": comp_rgb.detach(), **gout}

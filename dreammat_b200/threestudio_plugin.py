@@ -334,6 +334,24 @@ class DreamMat(BaseLift3DSystem):
         except Exception:      # outside a Trainer loop (tests, scripts) LightningModule.log is unavailable
             pass
 
+    def _save_train_images(self, out, batch) -> None:
+        """systems/dreammat.py:88-178: every `save_train_image_iter` steps one grid -- a row of eight render outputs and a row of
+        the condition map's eight channel groups (depth | normal | six light maps).  Needs the host's saver mixin."""
+        saver = getattr(self, "save_image_grid", None)
+        step = int(self.true_global_step)
+        if not self.cfg.save_train_image or saver is None or step % int(self.cfg.save_train_image_iter) != 0:
+            return
+
+        def cell(img, gray=False):
+            if gray:
+                return {"type": "grayscale", "img": img[..., 0], "kwargs": {"cmap": None, "data_range": (0, 1)}}
+            return {"type": "rgb", "img": img, "kwargs": {"data_format": "HWC", "data_range": (0, 1)}}
+        renders = [cell(out[k][0], k in ("comp_depth", "metalness", "roughness"))
+                   for k in ("comp_rgb", "specular_light", "diffuse_light", "comp_normal", "comp_depth", "albedo", "metalness", "roughness")]
+        cm = batch["condition_map"][0]
+        conditions = [cell(cm[:, :, 0:1], True)] + [cell(cm[:, :, c:c + 3]) for c in range(1, 22, 3)]
+        saver(f"train/it{step}.png", imgs=[renders, conditions], name="train_step", step=step)
+
     def training_step(self, batch, batch_idx):
         """systems/dreammat.py:57-86."""
         prompt_utils = self.prompt_processor()
@@ -353,15 +371,23 @@ class DreamMat(BaseLift3DSystem):
                 if name.startswith("loss_"):
                     self._log(f"train/{name}", value)
                     loss = loss + value * self.C(self.cfg.loss[name.replace("loss_", "lambda_")])
+            for name, value in self.cfg.loss.items():
+                self._log(f"train_params/{name}", self.C(value))
+            self._save_train_images(out, batch)
             return {"loss": loss}
         impl, geo = self.impl, self.geometry.impl
         impl.prompt_utils = prompt_utils
         impl.global_step = step                       # schedules (C(...)) follow the trainer's step counter
         out = impl.training_step_fused(batch, apply_optimizer=False)
-        for k in ("loss_sds", "loss_mat_reg", "grad_norm"):
-            self._log(f"train/{k}", out[k])
+        for k, v in out.items():      # same keys as the reference logs: loss_sds, grad_norm, the 8 diagnostic norms, loss_mat_reg
+            if k.startswith("loss_") or k.endswith("_norm"):
+                self._log(f"train/{k}", v)
         for name, value in self.cfg.loss.items():
             self._log(f"train_params/{name}", self.C(value))
+        if (self.cfg.save_train_image and hasattr(self, "save_image_grid") and "condition_map" in batch
+                and step % int(self.cfg.save_train_image_iter) == 0):
+            with torch.no_grad():         # the fused step keeps no aux maps: the monitoring grid renders them on its (rare) steps
+                self._save_train_images(self(batch), batch)
         p = self.geometry
         loss = _FusedStepLoss.apply(out["loss"], None, p.encoding.encoding.encoding.params, p.feature_network.layers[0].weight,
                                     p.feature_network.layers[2].weight, geo.dgrid, geo.dW1, geo.dW2)

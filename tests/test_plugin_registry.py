@@ -261,3 +261,84 @@ def test_vae_legacy_attention_keys_and_config_json(tmp_path):
     (tmp_path / "v.json").write_text(json.dumps({"block_out_channels": [128, 256, 512, 512], "latent_channels": 4, "scaling_factor": 0.18215}))
     assert W.vae_config_from_json(str(tmp_path / "v.json")) == W.VAEConfig()
     assert W.unet_config_from_json("/nonexistent") == W.UNetConfig()
+
+
+def test_training_step_host_logic_matches_reference_execution(stub_on_path):
+    """The plugin system's training_step against a record of the reference's own `DreamMat.training_step`
+    (systems/dreammat.py:57-179) executed with recording stand-ins (tests/golden/make_system_golden.py): what the guidance is
+    handed, the loss assembly with scheduled weights, the names / order / values of everything logged, and the train-image grid.
+    Both branches: op-by-op (`fused_step=False`) and fused (the kernel sequence stood in by a stub returning the same numbers)."""
+    import types
+
+    import dreammat_b200.threestudio_plugin as P
+    from dreammat_b200.guidance import C
+    from tests.golden.make_system_golden import scenario
+    G = torch.load(os.path.join(ROOT, "tests", "golden", "system_vectors.pt"))
+    for rec in G["records"]:
+        step = rec["step"]
+        for fused in (False, True):
+            out, gout, batch = scenario(step)
+            log, grids, seen = [], [], {}
+
+            class Sys:
+                cfg = types.SimpleNamespace(loss=dict(G["loss_cfg"]), save_train_image=True, save_train_image_iter=rec["save_iter"],
+                                            texture=True, fused_step=fused)
+                true_global_step, true_current_epoch = step, 0
+                training_step, _log, _save_train_images = P.DreamMat.training_step, P.DreamMat._log, P.DreamMat._save_train_images
+
+                def __call__(self, b):
+                    seen["renderer_batch_keys"] = sorted(b)
+                    return out
+
+                def prompt_processor(self):
+                    return "PROMPT_UTILS"
+
+                def log(self, name, value):
+                    log.append((name, float(value)))
+
+                def C(self, v):
+                    return C(v, self.true_current_epoch, self.true_global_step)
+
+                def guidance(self, rgb, prompt_utils, **kw):
+                    seen["guidance"] = dict(rgb_is_comp_rgb=rgb is out["comp_rgb"], prompt_utils=prompt_utils, keys=sorted(kw),
+                                            cond_normal_is_comp_normal=kw.get("cond_normal") is out["comp_normal"],
+                                            cond_depth_is_comp_depth=kw.get("cond_depth") is out["comp_depth"], rgb_as_latents=kw.get("rgb_as_latents"))
+                    return dict(gout, _grad=torch.zeros(1))        # the product's guidance also returns private `_` entries: never logged
+
+                def save_image_grid(self, fn, imgs=None, name=None, step=None):
+                    grids.append(dict(filename=fn, name=name, step=step, rows=imgs))
+            me = Sys()
+            if fused:
+                lam = {k: C(v, 0, step) for k, v in G["loss_cfg"].items()}
+                flat = torch.zeros(6, requires_grad=True)
+
+                class Impl:        # stands for system.DreamMat: same numbers as the op-by-op branch would produce
+                    def training_step_fused(self, b, apply_optimizer=True):
+                        assert apply_optimizer is False
+                        return {"loss": lam["lambda_sds"] * gout["loss_sds"] + lam["lambda_mat_reg"] * out["loss_mat_reg"], "loss_sds": gout["loss_sds"],
+                                "loss_mat_reg": out["loss_mat_reg"], "comp_rgb": out["comp_rgb"], **{k: v for k, v in gout.items() if k.endswith("_norm")}}
+                me.impl = Impl()
+                layers = [types.SimpleNamespace(weight=flat[2:4]), None, types.SimpleNamespace(weight=flat[4:6])]
+                me.geometry = types.SimpleNamespace(impl=types.SimpleNamespace(dgrid=torch.ones(2), dW1=torch.ones(2), dW2=torch.ones(2)),
+                                                    encoding=types.SimpleNamespace(encoding=types.SimpleNamespace(encoding=types.SimpleNamespace(params=flat[0:2]))),
+                                                    feature_network=types.SimpleNamespace(layers=layers))
+            ret = me.training_step(dict(batch), 0)
+            assert abs(float(ret["loss"]) - rec["loss"]) < 1e-5 * max(1.0, abs(rec["loss"])), (step, fused, float(ret["loss"]), rec["loss"])
+            want = dict(rec["log"])
+            got = dict(log)
+            assert set(got) == set(want), (step, fused, sorted(set(got) ^ set(want)))
+            for k, v in want.items():
+                assert abs(got[k] - v) < 1e-5 * max(1.0, abs(v)), (k, got[k], v)
+            if not fused:
+                assert [n for n, _ in log] == [n for n, _ in rec["log"]]                      # same order, too
+                assert seen == rec["seen"]
+            else:
+                ret["loss"].backward()                                                     # the carried gradient reaches the leaves
+                assert torch.equal(flat.grad, torch.ones(6))
+            assert len(grids) == len(rec["grids"])
+            for ours, ref in zip(grids, rec["grids"]):
+                assert (ours["filename"], ours["name"], ours["step"]) == (ref["filename"], ref["name"], ref["step"])
+                assert [len(r) for r in ours["rows"]] == [len(r) for r in ref["rows"]] == [8, 8]
+                for ro, rr in zip(ours["rows"], ref["rows"]):
+                    for co, cr in zip(ro, rr):
+                        assert co["type"] == cr["type"] and co["kwargs"] == cr["kwargs"] and torch.equal(co["img"], cr["img"])
