@@ -341,11 +341,7 @@ class DreamMat(BaseLift3DSystem):
         step = int(self.true_global_step)
         if not self.cfg.save_train_image or saver is None or step % int(self.cfg.save_train_image_iter) != 0:
             return
-
-        def cell(img, gray=False):
-            if gray:
-                return {"type": "grayscale", "img": img[..., 0], "kwargs": {"cmap": None, "data_range": (0, 1)}}
-            return {"type": "rgb", "img": img, "kwargs": {"data_format": "HWC", "data_range": (0, 1)}}
+        cell = DreamMat._cell
         renders = [cell(out[k][0], k in ("comp_depth", "metalness", "roughness"))
                    for k in ("comp_rgb", "specular_light", "diffuse_light", "comp_normal", "comp_depth", "albedo", "metalness", "roughness")]
         cm = batch["condition_map"][0]
@@ -393,11 +389,40 @@ class DreamMat(BaseLift3DSystem):
                                     p.feature_network.layers[2].weight, geo.dgrid, geo.dW1, geo.dW2)
         return {"loss": loss, "comp_rgb": out["comp_rgb"]}
 
-    def validation_step(self, batch, batch_idx):
-        return self(batch)
+    @staticmethod
+    def _cell(img, gray=False):
+        if gray:
+            return {"type": "grayscale", "img": img[..., 0], "kwargs": {"cmap": None, "data_range": (0, 1)}}
+        return {"type": "rgb", "img": img, "kwargs": {"data_format": "HWC", "data_range": (0, 1)}}
 
-    def test_step(self, batch, batch_idx):
-        return self(batch)
+    def _grid(self, out, keys):
+        cells = [self._cell(out["comp_rgb"][0].detach())] if self.cfg.texture else []
+        return cells + [self._cell(out[k][0], k in ("metalness", "roughness")) for k in keys]
+
+    def validation_step(self, batch, batch_idx=None):
+        """systems/dreammat.py:181-240: one grid per validation view (render | lights | colours | normal | albedo | metalness | roughness)."""
+        out = self(batch)
+        step = self.true_global_step
+        self.save_image_grid(f"validate/it{step}-{batch['index'][0]}.png",
+                             self._grid(out, ("specular_light", "diffuse_light", "specular_color", "diffuse_color", "comp_normal", "albedo",
+                                              "metalness", "roughness")), name="validation_step", step=step)
 
     def on_validation_epoch_end(self):
         pass
+
+    def test_step(self, batch, batch_idx=None):
+        """systems/dreammat.py:245-296: the per-view grid plus the four RGBA maps (albedo / roughness / metallic / render, alpha =
+        opacity) the texture baker reads."""
+        out = self(batch)
+        step, idx = self.true_global_step, batch["index"][0]
+        self.save_image_grid(f"it{step}-test/view/{idx}.png", self._grid(out, ("comp_normal", "albedo", "metalness", "roughness")),
+                             name="test_step", step=step)
+        mask = out["opacity"][0].detach()
+        maps = {"albedo": out["albedo"][0].detach(), "roughness": out["roughness"][0].detach().repeat(1, 1, 3),
+                "metallic": out["metalness"][0].detach().repeat(1, 1, 3), "render": out["comp_rgb"][0].detach()}
+        for name, img in maps.items():
+            self.save_img(torch.cat((img, mask), 2), f"it{step}-test/{name}/{idx}.png")
+
+    def on_test_epoch_end(self):
+        """systems/dreammat.py:298-300"""
+        self.save_gif("it" + str(self.true_global_step) + "-test/view", fps=30)

@@ -5,7 +5,8 @@ the renderer, the guidance, Lightning's `self.log` and the saver's `self.save_im
 What it pins: which keys the step hands to the guidance (`cond_normal`, `cond_depth` added to the batch, `rgb_as_latents=False`),
 the loss assembly (`loss_* x C(lambda_*)` over the guidance outputs, then over the renderer outputs), the order and names of
 everything logged, and the layout of the train-image grid (two rows: eight render outputs, eight channel groups of the
-22-channel condition map).
+22-channel condition map); and, for `validation_step` / `test_step` / `on_test_epoch_end` (:181-300), the file names, grid
+layouts, the four RGBA maps written per test view and the turntable gif call.
 
 Run from the repo root where /root/reference exists:  python tests/golden/make_system_golden.py -> system_vectors.pt
 """
@@ -48,7 +49,7 @@ def main():
     lift("systems/base.py", ["C"], ns, cls="BaseSystem")
     ns["C_method"] = ns["C"]            # BaseSystem.C; the free function C it calls (utils/misc.py) takes the name back
     ns["C"] = nc["C"]
-    lift("systems/dreammat.py", ["training_step"], ns, cls="DreamMat")
+    lift("systems/dreammat.py", ["training_step", "validation_step", "test_step", "on_test_epoch_end"], ns, cls="DreamMat")
     records = []
     for step, save_iter in ((0, 1), (400, 1000), (3000, 1000)):
         out, gout, batch = scenario(step)
@@ -73,7 +74,23 @@ def main():
         me.bind(ns, ["training_step"])
         ret = me.training_step(dict(batch), 0)
         records.append(dict(step=step, save_iter=save_iter, loss=float(ret["loss"]), ret_keys=sorted(ret), log=log, grids=grids, seen=seen))
-    torch.save({"loss_cfg": LOSS, "records": records}, OUT)
+    # validation / test hooks (:181-300): grids per view, the four RGBA maps the texture baker reads, the turntable gif
+    evals = []
+    for texture in (True, False):
+        out, _, batch = scenario(77)
+        batch["index"] = torch.tensor([7])
+        calls = []
+        me = Fake(cfg=Fake(texture=texture), true_global_step=1234)
+        me.__class__ = type("S", (Fake,), {"__call__": lambda self, b: out})
+        me.save_image_grid = lambda fn, imgs=None, name=None, step=None: calls.append(("grid", fn, name, step, [dict(type=c["type"], kwargs=c["kwargs"], img=c["img"].clone()) for c in imgs]))
+        me.save_img = lambda img, fn: calls.append(("img", fn, img.clone()))
+        me.save_gif = lambda path, fps=None: calls.append(("gif", path, fps))
+        me.bind(ns, ["validation_step", "test_step", "on_test_epoch_end"])
+        me.validation_step(batch)
+        me.test_step(batch)
+        me.on_test_epoch_end()
+        evals.append(dict(texture=texture, calls=calls))
+    torch.save({"loss_cfg": LOSS, "records": records, "evals": evals}, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", [(r["step"], round(r["loss"], 4), len(r["log"]), len(r["grids"])) for r in records])
 
 

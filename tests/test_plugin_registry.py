@@ -342,3 +342,52 @@ def test_training_step_host_logic_matches_reference_execution(stub_on_path):
                 for ro, rr in zip(ours["rows"], ref["rows"]):
                     for co, cr in zip(ro, rr):
                         assert co["type"] == cr["type"] and co["kwargs"] == cr["kwargs"] and torch.equal(co["img"], cr["img"])
+
+
+def test_validation_and_test_hooks_match_reference_execution(stub_on_path):
+    """validation_step / test_step / on_test_epoch_end of the plugin system against a record of the reference's own hooks
+    (systems/dreammat.py:181-300): file names, grid layouts with and without `texture`, the four RGBA maps per test view
+    (albedo / roughness / metallic / render over the opacity), the turntable gif."""
+    import types
+
+    import dreammat_b200.threestudio_plugin as P
+    from tests.golden.make_system_golden import scenario
+    G = torch.load(os.path.join(ROOT, "tests", "golden", "system_vectors.pt"))
+    assert [e["texture"] for e in G["evals"]] == [True, False]
+    for ev in G["evals"]:
+        out, _, batch = scenario(77)
+        batch["index"] = torch.tensor([7])
+        calls = []
+
+        class Sys:
+            cfg = types.SimpleNamespace(texture=ev["texture"])
+            true_global_step = 1234
+            validation_step, test_step, on_test_epoch_end = P.DreamMat.validation_step, P.DreamMat.test_step, P.DreamMat.on_test_epoch_end
+            _grid, _cell = P.DreamMat._grid, staticmethod(P.DreamMat._cell)
+
+            def __call__(self, b):
+                return out
+
+            def save_image_grid(self, fn, imgs=None, name=None, step=None):
+                calls.append(("grid", fn, name, step, imgs))
+
+            def save_img(self, img, fn):
+                calls.append(("img", fn, img))
+
+            def save_gif(self, path, fps=None):
+                calls.append(("gif", path, fps))
+        me = Sys()
+        me.validation_step(batch)
+        me.test_step(batch)
+        me.on_test_epoch_end()
+        assert len(calls) == len(ev["calls"]) == 7
+        for ours, ref in zip(calls, ev["calls"]):
+            assert ours[0] == ref[0] and ours[1] == ref[1], (ours[:2], ref[:2])
+            if ours[0] == "grid":
+                assert ours[2:4] == ref[2:4] and len(ours[4]) == len(ref[4])
+                for co, cr in zip(ours[4], ref[4]):
+                    assert co["type"] == cr["type"] and co["kwargs"] == cr["kwargs"] and torch.equal(co["img"], cr["img"])
+            elif ours[0] == "img":
+                assert ours[2].shape[-1] == 4 and torch.equal(ours[2], ref[2])
+            else:
+                assert ours[2] == ref[2] == 30
