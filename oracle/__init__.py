@@ -18,7 +18,13 @@ oracle against the resulting vectors (tests/golden/reference_vectors.pt) for
   a4  DreamMatMaterial.forward -> shade_raytracing, forward AND autograd backward, with the
       reference's sampling tables, env lookup and occlusion semantics (dreammat_material.py),
   a8/a9  the CSD combination, loss_sds and its gradient (dreammat_guidance.py:440-497, 584-602),
-  schedules C(), vertex normals, material export.
+  schedules C(), vertex normals, material export;
+and, executed END TO END with the oracle's own pieces standing in for the absent native calls
+(tests/golden/make_renderer_golden.py, make_guidance_golden.py, make_splitsum_golden.py),
+  a2/a3/a6  the whole RaytraceRender.forward composition (raytracing_renderer.py:110-222) -> render_forward,
+  a5        DreamMatMaterial.forward(use_raytracing=False) -> shade_splitsum on the real FG LUT, forward + backward,
+  a7-a9     the whole StableDiffusionLightGuidance.__call__ and update_step over dreammat.yaml's schedules
+            (dreammat_guidance.py:205-316,388-640) -> sd.guidance_step: loss, logged norms, d loss / d rgb.
 PARITY UNPINNED for the arithmetic that lives inside absent native packages -- tiny-cuda-nn
 hash grid, nvdiffrast rasterise / antialias / texture, envlight cube maps, the _raytracing BVH,
 diffusers UNet / ControlNet / VAE: restated from their published form and pinned only by
