@@ -37,7 +37,8 @@ def test_single_gpu_line_has_the_contract_keys():
         assert k in d["cpu_baseline"], k
     assert d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] > 500
     ss = d["cpu_baseline"]["sample_seconds"]          # every unit measured at its real size
-    assert {"unet_controlnet_1sample_64x64_latents", "vae_512_fwd_bwd", "shade_128x128_render"} <= set(ss)
+    assert {"vae_512_fwd_bwd", "shade_128x128_render"} <= set(ss)
+    assert {"unet_controlnet_1sample_64x64_latents", "unet_controlnet_3branch_batch_64x64_latents"} & set(ss)   # r02 line: per sample; later: per view
     gb = d["gpu_baseline"]                            # the "same box" bar: stock PyTorch CUDA ops
     assert gb["dense_ms"] > 0 and gb["ours_over_stock"]["dense"] > 1.0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
