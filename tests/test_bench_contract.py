@@ -62,3 +62,19 @@ def test_multi_gpu_lines():
         assert pc["grad_rel_err_fp32_mode"] < 1e-3          # the crisp identity: fp32 high-precision dense half
     w = _line("r02_bench_8gpu_config4_64views.json")
     assert w["n_gpus"] == 8 and w["scaling"] == "weak" and w["config"]["views"] == 64
+
+
+def test_readme_numbers_are_the_committed_lines():
+    """The headline table of README.md quotes the committed bench lines, not remembered values."""
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    d1 = _line("r02_bench_1gpu.json")
+    assert f"**{d1['value']:.2f}** it/s" in readme and f"{d1['e2e']['value']:.2f} it/s" in readme
+    assert f"{d1['e2e']['h2d_bytes_per_step']} B host-to-device" in readme
+    d2, d4, d8 = _line("r02_bench_2gpu_check_balanced.json"), _line("r02_bench_4gpu.json"), _line("r02_bench_8gpu.json")
+    assert f"{d2['value']:.1f} / {d4['value']:.1f} / {d8['value']:.1f} it/s" in readme
+    w = _line("r02_bench_8gpu_config4_64views.json")
+    assert f"{w['value']:.2f} it/s" in readme
+    c2, c3, ss = _line("r02_bench_config2.json"), _line("r02_bench_config3.json"), _line("r02_bench_splitsum.json")
+    assert f"{c2['value']:.1f} / {c3['value']:.2f} / {ss['value']:.1f} it/s" in readme
+    gb = d1["gpu_baseline"]
+    assert f"{gb['ours_over_stock']['dense']:.2f} x" in readme
