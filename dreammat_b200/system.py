@@ -592,9 +592,10 @@ class DreamMat:
             check(lib().dm_resize_bilinear(ptr(dvae.contiguous()), B, H, W, 512, 512, 3, ptr(dcanvas), 1, st), "dm_resize_bilinear")
         else:
             dcanvas = dvae.reshape(B, H * W, 3)
-        n = sums.sqrt()       # the reference logs all of these every step (systems/dreammat.py:72-74 over compute_grad_sds' dict)
-        gout = {"grad_norm": n[1], "uncond_m_noise_norm": n[2], "text_m_noise_norm": n[3], "text_m_uncond_norm": n[4],
-                "text_m_null_norm": n[5], "null_m_uncond_norm": n[6], "noise_norm": n[7], "uncond_norm": n[8], "text_norm": n[9]}
+        nrms = sums.sqrt()    # the reference logs all of these every step (systems/dreammat.py:72-74 over compute_grad_sds' dict)
+        gout = {"grad_norm": nrms[1], "uncond_m_noise_norm": nrms[2], "text_m_noise_norm": nrms[3], "text_m_uncond_norm": nrms[4],
+                "text_m_null_norm": nrms[5], "null_m_uncond_norm": nrms[6], "noise_norm": nrms[7], "uncond_norm": nrms[8],
+                "text_norm": nrms[9]}
         # backward into the hash grid / MLP
         geo.grads.zero_()
         dcolor_own = torch.empty(max(own_px, 1), 3, device=dev)
